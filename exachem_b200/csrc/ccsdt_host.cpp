@@ -1,0 +1,252 @@
+#include "ccsdt_host.hpp"
+
+#include <algorithm>
+#include <numeric>
+
+namespace ccsdt {
+
+// ------------------------------------------------------------------------------------------------
+// term tables (signs and index roles of the 27 equations; SURVEY.md §8 a9, reference statement
+// exachem/cc/ccsd_t/ccsd_t_all_fused_cpu.hpp:172-270, 330-428, 472-578)
+//                       pa pb hx hy hz pc sign
+const D1Term kD1[9] = {{3, 4, 0, 1, 2, 5, -1}, {3, 4, 1, 0, 2, 5, +1}, {3, 4, 2, 0, 1, 5, -1},
+                       {4, 5, 0, 1, 2, 3, -1}, {4, 5, 1, 0, 2, 3, +1}, {4, 5, 2, 0, 1, 3, -1},
+                       {3, 5, 0, 1, 2, 4, +1}, {3, 5, 1, 0, 2, 4, -1}, {3, 5, 2, 0, 1, 4, +1}};
+//                       pa hx hy hz pb pc sign
+const D2Term kD2[9] = {{3, 0, 1, 2, 4, 5, -1}, {3, 1, 2, 0, 4, 5, -1}, {3, 0, 2, 1, 4, 5, +1},
+                       {4, 0, 1, 2, 3, 5, +1}, {4, 1, 2, 0, 3, 5, +1}, {4, 0, 2, 1, 3, 5, -1},
+                       {5, 0, 1, 2, 3, 4, -1}, {5, 1, 2, 0, 3, 4, -1}, {5, 0, 2, 1, 3, 4, +1}};
+//                       pa hx hy hz pb pc sign
+const S1Term kS1[9] = {{3, 0, 1, 2, 4, 5, +1}, {3, 1, 0, 2, 4, 5, -1}, {3, 2, 0, 1, 4, 5, +1},
+                       {4, 0, 1, 2, 3, 5, -1}, {4, 1, 0, 2, 3, 5, +1}, {4, 2, 0, 1, 3, 5, -1},
+                       {5, 0, 1, 2, 3, 4, +1}, {5, 1, 0, 2, 3, 4, -1}, {5, 2, 0, 1, 3, 4, +1}};
+
+// ------------------------------------------------------------------------------------------------
+int64_t Space::max_hole_tile() const {
+  int64_t m = 0;
+  for(int i = 0; i < noab(); i++) m = std::max(m, k_range[i]);
+  return m;
+}
+int64_t Space::max_particle_tile() const {
+  int64_t m = 0;
+  for(int i = noab(); i < noab() + nvab(); i++) m = std::max(m, k_range[i]);
+  return m;
+}
+
+void Space::spin_range(bool particle, int spin, int& tile_begin, int& tile_end, int64_t& n_orb) const {
+  const int lo = particle ? noab() : 0, hi = particle ? noab() + nvab() : noab();
+  tile_begin = hi;
+  tile_end   = hi;
+  n_orb      = 0;
+  for(int t = lo; t < hi; t++) {
+    if(k_spin[t] != spin) continue;
+    if(tile_begin == hi) tile_begin = t;
+    tile_end = t + 1;
+    n_orb += k_range[t];
+  }
+  if(tile_begin == hi) tile_begin = tile_end = lo;
+}
+
+std::string Space::validate() const {
+  const int n = noab() + nvab();
+  if(noab() <= 0 || nvab() <= 0) return "empty occupied or virtual tile space";
+  if((int) k_range.size() != n || (int) k_spin.size() != n) return "k_range/k_spin length mismatch";
+  for(int t = 0; t < n; t++) {
+    if(k_range[t] <= 0) return "tile with non-positive extent";
+    if(k_spin[t] != 1 && k_spin[t] != 2) return "k_spin entries must be 1 (alpha) or 2 (beta)";
+  }
+  // tiles of one spin must be contiguous inside occ and inside virt (| a | b | ordering)
+  for(int part = 0; part < 2; part++) {
+    const int lo = part ? noab() : 0, hi = part ? n : noab();
+    int       changes = 0;
+    for(int t = lo + 1; t < hi; t++) changes += k_spin[t] != k_spin[t - 1];
+    if(changes > 1) return "tiles of equal spin are not contiguous";
+    if(changes == 1 && k_spin[lo] != 1) return "alpha tiles must precede beta tiles";
+  }
+  if((int64_t) evl.size() != k_offset.back()) return "orbital-energy vector length mismatch";
+  return "";
+}
+
+Space make_space(int noa, int nob, int nva, int nvb, const int64_t* k_range, const int32_t* k_spin,
+                 const double* evl, bool restricted) {
+  Space s;
+  s.noa = noa, s.nob = nob, s.nva = nva, s.nvb = nvb, s.restricted = restricted;
+  const int n   = noa + nob + nva + nvb;
+  int64_t   sum = 0;
+  for(int t = 0; t < n; t++) {
+    s.k_range.push_back(k_range[t]);
+    s.k_offset.push_back(sum);
+    s.k_spin.push_back(k_spin[t]);
+    sum += k_range[t];
+  }
+  s.k_offset.push_back(sum);
+  if(evl) s.evl.assign(evl, evl + sum);
+  else s.evl.assign((size_t) sum, 0.0);
+  return s;
+}
+
+int make_tiles(int64_t n_occ_alpha, int64_t n_occ_beta, int64_t n_vir_alpha, int64_t n_vir_beta,
+               int64_t tilesize, std::vector<int64_t>& k_range, std::vector<int32_t>& k_spin,
+               int32_t counts[4]) {
+  k_range.clear();
+  k_spin.clear();
+  const int64_t n[4] = {n_occ_alpha, n_occ_beta, n_vir_alpha, n_vir_beta};
+  for(int g = 0; g < 4; g++) {
+    int c = 0;
+    for(int64_t left = n[g]; left > 0; left -= tilesize, c++) k_range.push_back(std::min(left, tilesize));
+    counts[g] = c;
+  }
+  // spins: first half of the occupied (virtual) tiles alpha, second half beta -- the reference does
+  // not look at the actual alpha/beta tile counts here
+  const int noab = counts[0] + counts[1], nvab = counts[2] + counts[3];
+  for(int x = 0; x < noab; x++) k_spin.push_back(x < noab / 2 ? 1 : 2);
+  for(int x = 0; x < nvab; x++) k_spin.push_back(x < nvab / 2 ? 1 : 2);
+  return (int) k_range.size();
+}
+
+// ------------------------------------------------------------------------------------------------
+static double symmetry_factor(bool restricted, const int32_t t[6]) {
+  double f = restricted ? 2.0 : 1.0;
+  if(t[3] == t[4] && t[4] == t[5]) f /= 6.0;
+  else if(t[3] == t[4] || t[4] == t[5]) f /= 2.0;
+  if(t[0] == t[1] && t[1] == t[2]) f /= 6.0;
+  else if(t[0] == t[1] || t[1] == t[2]) f /= 2.0;
+  return f;
+}
+
+static bool spin_allowed(const int32_t* k_spin, bool restricted, const int32_t t[6]) {
+  const int sh = k_spin[t[0]] + k_spin[t[1]] + k_spin[t[2]];
+  const int sp = k_spin[t[3]] + k_spin[t[4]] + k_spin[t[5]];
+  return sh == sp && (!restricted || sh + sp <= 8);
+}
+
+std::vector<Task> enumerate_tasks(int noab, int nvab, const int32_t* k_spin, bool restricted,
+                                  int64_t* n_outer) {
+  std::vector<Task> out;
+  int64_t           outer = 0;
+  const int         pend  = noab + nvab;
+  // distribution order of the reference: (h1b, p4b, h2b>=h1b, p5b>=p4b, p6b>=p5b) outer 5-tuples,
+  // h3b>=h2b innermost
+  for(int h1 = 0; h1 < noab; h1++)
+    for(int p4 = noab; p4 < pend; p4++)
+      for(int h2 = h1; h2 < noab; h2++)
+        for(int p5 = p4; p5 < pend; p5++)
+          for(int p6 = p5; p6 < pend; p6++, outer++)
+            for(int h3 = h2; h3 < noab; h3++) {
+              Task t{{h1, h2, h3, p4, p5, p6}, outer, 0.0};
+              if(!spin_allowed(k_spin, restricted, t.t)) continue;
+              t.factor = symmetry_factor(restricted, t.t);
+              out.push_back(t);
+            }
+  if(n_outer) *n_outer = outer;
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+static inline int spin_of(const Space& sp, const Task& t, int idx) { return sp.k_spin[t.t[idx]]; }
+
+bool task_nonempty(const Space& sp, const Task& t) {
+  for(int i = 0; i < 6; i++)
+    if(sp.k_range[t.t[i]] <= 0) return false;
+  int sum = 0;
+  for(int i = 0; i < 6; i++) sum += spin_of(sp, t, i);
+  // the reference skips all-beta sextuples in restricted mode inside its staging functions too
+  return !(sp.restricted && sum == 12);
+}
+
+int d1_contracted_spin(const Space& sp, const Task& t, int k) {
+  if(!task_nonempty(sp, t)) return 0;
+  const int s = spin_of(sp, t, kD1[k].pa) + spin_of(sp, t, kD1[k].pb) - spin_of(sp, t, kD1[k].hx);
+  return (s == 1 || s == 2) ? s : 0;
+}
+int d2_contracted_spin(const Space& sp, const Task& t, int k) {
+  if(!task_nonempty(sp, t)) return 0;
+  const int s = spin_of(sp, t, kD2[k].hx) + spin_of(sp, t, kD2[k].hy) - spin_of(sp, t, kD2[k].pa);
+  return (s == 1 || s == 2) ? s : 0;
+}
+bool s1_enabled(const Space& sp, const Task& t, int k) {
+  return task_nonempty(sp, t) && spin_of(sp, t, kS1[k].pa) == spin_of(sp, t, kS1[k].hx);
+}
+
+void task_terms(const Space& sp, const Task& t, uint8_t* s1_on, uint8_t* d1_on, uint8_t* d2_on) {
+  const int noab = sp.noab(), nvab = sp.nvab();
+  for(int k = 0; k < 9; k++) s1_on[k] = s1_enabled(sp, t, k);
+  for(int k = 0; k < 9; k++) {
+    const int s = d1_contracted_spin(sp, t, k);
+    for(int h7 = 0; h7 < noab; h7++) d1_on[k + 9 * h7] = (s != 0 && sp.k_spin[h7] == s);
+  }
+  for(int k = 0; k < 9; k++) {
+    const int s = d2_contracted_spin(sp, t, k);
+    for(int p7 = 0; p7 < nvab; p7++) d2_on[k + 9 * p7] = (s != 0 && sp.k_spin[noab + p7] == s);
+  }
+}
+
+static void task_ops_split(const Space& sp, const Task& t, long double& s1, long double& d1,
+                           long double& d2) {
+  long double base = 2;
+  for(int i = 0; i < 6; i++) base *= (long double) sp.k_range[t.t[i]];
+  s1 = d1 = d2 = 0;
+  for(int k = 0; k < 9; k++)
+    if(s1_enabled(sp, t, k)) s1 += base;
+  int     tb, te;
+  int64_t n;
+  for(int k = 0; k < 9; k++) {
+    const int s = d1_contracted_spin(sp, t, k);
+    if(!s) continue;
+    sp.spin_range(false, s, tb, te, n);
+    for(int h7 = tb; h7 < te; h7++) d1 += base * (long double) sp.k_range[h7];
+  }
+  for(int k = 0; k < 9; k++) {
+    const int s = d2_contracted_spin(sp, t, k);
+    if(!s) continue;
+    sp.spin_range(true, s, tb, te, n);
+    for(int p7 = tb; p7 < te; p7++) d2 += base * (long double) sp.k_range[p7];
+  }
+}
+
+long double task_ops(const Space& sp, const Task& t) {
+  long double a, b, c;
+  task_ops_split(sp, t, a, b, c);
+  return a + b + c;
+}
+
+long double count_ops(const Space& sp) {
+  // same accumulation structure as the reference's counter (three running totals, task order
+  // p4b,p5b,p6b,h1b,h2b,h3b) so the long-double result is identical even beyond 2^64
+  long double tot_s1 = 0, tot_d1 = 0, tot_d2 = 0;
+  const int   noab = sp.noab(), pend = sp.noab() + sp.nvab();
+  for(int p4 = noab; p4 < pend; p4++)
+    for(int p5 = p4; p5 < pend; p5++)
+      for(int p6 = p5; p6 < pend; p6++)
+        for(int h1 = 0; h1 < noab; h1++)
+          for(int h2 = h1; h2 < noab; h2++)
+            for(int h3 = h2; h3 < noab; h3++) {
+              Task t{{h1, h2, h3, p4, p5, p6}, 0, 0.0};
+              if(!spin_allowed(sp.k_spin.data(), sp.restricted, t.t)) continue;
+              long double a, b, c;
+              task_ops_split(sp, t, a, b, c);
+              tot_s1 += a, tot_d1 += b, tot_d2 += c;
+            }
+  return tot_s1 + tot_d1 + tot_d2;
+}
+
+std::vector<int32_t> partition_tasks(const Space& sp, const std::vector<Task>& tasks, int nranks) {
+  std::vector<int32_t> owner(tasks.size(), 0);
+  if(nranks <= 1) return owner;
+  std::vector<long double> cost(tasks.size());
+  for(size_t i = 0; i < tasks.size(); i++) cost[i] = task_ops(sp, tasks[i]);
+  std::vector<size_t> order(tasks.size());
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cost[a] > cost[b]; });
+  std::vector<long double> load(nranks, 0);
+  for(size_t i: order) {
+    int best = 0;
+    for(int r = 1; r < nranks; r++)
+      if(load[r] < load[best]) best = r;
+    owner[i] = best;
+    load[best] += cost[i];
+  }
+  return owner;
+}
+
+} // namespace ccsdt

@@ -1,0 +1,81 @@
+// Host-side model of the (T) task space: tiles, spins, the canonical task list, which of the
+// 9 s1 + 9 d1 + 9 d2 contractions a task executes, the reference's flop count, and the static
+// cost-balanced split over ranks.  Pure C++17 (no CUDA) so that it is testable on a CPU-only box.
+//
+// Index ids everywhere: 0=h1 1=h2 2=h3 3=p4 4=p5 5=p6.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace ccsdt {
+
+struct Space {
+  int                  noa = 0, nob = 0, nva = 0, nvb = 0;
+  std::vector<int64_t> k_range, k_offset; // per tile, all tiles (occ a | occ b | virt a | virt b)
+  std::vector<int32_t> k_spin;            // 1 = alpha, 2 = beta
+  std::vector<double>  evl;               // orbital energies, spin-orbital order of the tiles
+  bool                 restricted = true;
+
+  int     noab() const { return noa + nob; }
+  int     nvab() const { return nva + nvb; }
+  int64_t n_occ() const { return k_offset[noab()]; }
+  int64_t n_virt() const { return k_offset.back() - k_offset[noab()]; }
+  int64_t max_hole_tile() const;
+  int64_t max_particle_tile() const;
+  // orbitals of one spin inside the occupied (particle=false) or virtual range: contiguous tiles
+  void    spin_range(bool particle, int spin, int& tile_begin, int& tile_end, int64_t& n_orb) const;
+  std::string validate() const; // empty = ok
+};
+
+Space make_space(int noa, int nob, int nva, int nvb, const int64_t* k_range, const int32_t* k_spin,
+                 const double* evl, bool restricted);
+
+// setupMOIS(triples=true) tiling + the half/half spin labels (see include/ccsdt_b200.h)
+int make_tiles(int64_t n_occ_alpha, int64_t n_occ_beta, int64_t n_vir_alpha, int64_t n_vir_beta,
+               int64_t tilesize, std::vector<int64_t>& k_range, std::vector<int32_t>& k_spin,
+               int32_t counts[4]);
+
+struct Task {
+  int32_t t[6];  // tile ids h1b,h2b,h3b,p4b,p5b,p6b
+  int64_t outer; // id of the (h1b,p4b,h2b,p5b,p6b) 5-tuple: the reference's unit of distribution
+  double  factor;
+};
+
+std::vector<Task> enumerate_tasks(int noab, int nvab, const int32_t* k_spin, bool restricted,
+                                  int64_t* n_outer);
+
+// ---- the 27 contractions ---------------------------------------------------------------------
+// d1_k:  t3 += sign * sum_l  T2[pa,pb,hx,l] * v2ijka[hy,hz,l,pc]     (hy<hz the other holes)
+// d2_k:  t3 += sign * sum_d  T2[pa,d,hx,hy] * v2iabc[hz,d,pb,pc]     (hx<hy, pb<pc)
+// s1_k:  t3s+= sign * T1[pa,hx] * v2ijab[hz,hy,pc,pb]                (hy<hz, pb<pc)
+struct D1Term {
+  int pa, pb, hx, hy, hz, pc, sign;
+};
+struct D2Term {
+  int pa, hx, hy, hz, pb, pc, sign;
+};
+struct S1Term {
+  int pa, hx, hy, hz, pb, pc, sign;
+};
+extern const D1Term kD1[9];
+extern const D2Term kD2[9];
+extern const S1Term kS1[9];
+
+// spin of the contracted index required by a d1/d2 term of this task (0 = term disabled)
+int d1_contracted_spin(const Space& sp, const Task& t, int k);
+int d2_contracted_spin(const Space& sp, const Task& t, int k);
+bool s1_enabled(const Space& sp, const Task& t, int k);
+bool task_nonempty(const Space& sp, const Task& t);
+
+// enabled masks in the reference's exec-table layout: s1[9], d1[k + 9*h7b], d2[k + 9*(p7b-noab)]
+void task_terms(const Space& sp, const Task& t, uint8_t* s1_on, uint8_t* d1_on, uint8_t* d2_on);
+
+// flops of one task / of the whole list, as the reference counts them
+long double task_ops(const Space& sp, const Task& t);
+long double count_ops(const Space& sp);
+
+// static split: longest-processing-time greedy on task_ops; owner[i] in [0,nranks)
+std::vector<int32_t> partition_tasks(const Space& sp, const std::vector<Task>& tasks, int nranks);
+
+} // namespace ccsdt

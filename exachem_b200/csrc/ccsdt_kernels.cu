@@ -1,0 +1,744 @@
+// sm_100a kernels of the fused CCSD(T) triples path.
+//
+//   gather_panels_kernel   : builds the K-major operand panels of one task from tensor blocks
+//                            (replaces hptt sort + pinned staging + H2D of the reference,
+//                             exachem/cc/ccsd_t/ccsd_t_all_fused_{singles,doubles1,doubles2}.hpp)
+//   fused_t_dmma_kernel    : the product kernel.  One CTA = one (2s1,2s2,2s3,8,8,8) box of the
+//                            t3 tile; TMA (128B swizzle) + mbarrier ring feeds FP64 DMMA m8n8k4;
+//                            all enabled d1/d2 terms accumulate in registers, s1 and the energy
+//                            denominators are applied in the epilogue, per-box partials are written
+//                            without atomics  (replaces ccsd_t_all_fused_gpu.cu:132-2564)
+//   fused_t_simple_kernel  : diagnostic one-thread-per-element FMA kernel over the same panels
+//   reduce_partials_kernel : fixed-order sum of the per-box partials (replaces hostEnergyReduce,
+//                            ccsd_t_all_fused.hpp:19-32)
+//   probes                 : FP64 DFMA / DMMA peak, DMMA fragment layout, TMA swizzle layout
+#include "ccsdt_device.hpp"
+
+#include <cstdio>
+
+namespace ccsdt {
+
+// =================================================================================================
+// small PTX wrappers
+// =================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t) __cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+// bounded wait: a pipeline bug must end in a trap (reported as a CUDA error), never in a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* error_flag, int tag) {
+  if(mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while(!mbar_try_wait(bar, parity)) {
+    if(clock64() - t0 > 4000000000ll) { // ~2 s
+      if(error_flag) atomicExch(error_flag, 0xDEAD0000u | (uint32_t) tag);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+               " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+// D = A(8x4,row) * B(4x8,col) + D.  lane holds a = A[lane>>2][lane&3], b = B[lane&3][lane>>2],
+// d0,d1 = D[lane>>2][2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// =================================================================================================
+// panel build
+// =================================================================================================
+__global__ void __launch_bounds__(256) gather_panels_kernel(const GatherDesc* __restrict__ descs,
+                                                            SynthInfo si) {
+  const GatherDesc& d  = descs[blockIdx.y];
+  const int64_t     n3 = d.n[3], n2 = d.n[2], n1 = d.n[1];
+  const int64_t     total = (int64_t) d.n[0] * n1 * n2 * n3;
+  for(int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < total;
+      e += (int64_t) gridDim.x * blockDim.x) {
+    const int64_t k  = e % n3;
+    int64_t       r  = e / n3;
+    const int64_t in = r % n2;
+    r /= n2;
+    const int64_t o1 = r % n1, o2 = r / n1;
+    double        v;
+    if(d.synth_tensor >= 0) {
+      int64_t idx[4] = {0, 0, 0, 0};
+      idx[d.gpos[0]] = d.gbase[0] + o2;
+      idx[d.gpos[1]] = d.gbase[1] + o1;
+      idx[d.gpos[2]] = d.gbase[2] + in;
+      idx[d.gpos[3]] = d.gbase[3] + k;
+      v              = d.scale * synth_value(si, d.synth_tensor, idx);
+    }
+    else if(d.src) { v = d.scale * __ldg(d.src + o2 * d.ss[0] + o1 * d.ss[1] + in * d.ss[2] + k * d.ss[3]); }
+    else { v = 0.0; }
+    d.dst[o2 * d.ds[0] + o1 * d.ds[1] + in * d.ds[2] + k * d.ds[3]] = v;
+  }
+}
+
+cudaError_t launch_gather(const GatherDesc* dev_descs, int ndesc, int64_t max_elems, SynthInfo si,
+                          cudaStream_t st) {
+  if(ndesc <= 0) return cudaSuccess;
+  int64_t bx = (max_elems + 256 * 8 - 1) / (256 * 8);
+  if(bx < 1) bx = 1;
+  if(bx > 1024) bx = 1024;
+  for(int off = 0; off < ndesc; off += 65535) {
+    const int n = ndesc - off < 65535 ? ndesc - off : 65535;
+    gather_panels_kernel<<<dim3((unsigned) bx, (unsigned) n), 256, 0, st>>>(dev_descs + off, si);
+  }
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// shared epilogue pieces
+// =================================================================================================
+__device__ __forceinline__ double s1_sum(const TaskParams& p, const int coord[6]) {
+  double s = 0.0;
+  for(int k = 0; k < p.ns1; k++) {
+    const S1Dev& t  = p.s1[k];
+    int          oa = 0, ob = 0;
+#pragma unroll
+    for(int i = 0; i < 6; i++) {
+      oa += coord[i] * t.sa[i];
+      ob += coord[i] * t.sb[i];
+    }
+    s += __ldg(t.a + oa) * __ldg(t.b + ob);
+  }
+  return s;
+}
+
+// =================================================================================================
+// diagnostic kernel: one thread per t3 element, plain FMAs over the same panels
+// =================================================================================================
+__global__ void __launch_bounds__(256) fused_t_simple_kernel(const __grid_constant__ TaskParams p) {
+  __shared__ double red[2][8];
+  const int64_t total = (int64_t) p.ext[0] * p.ext[1] * p.ext[2] * p.ext[3] * p.ext[4] * p.ext[5];
+  const int64_t e     = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  double        e1 = 0.0, e2 = 0.0;
+  if(e < total) {
+    int     coord[6];
+    int64_t r = e;
+    // h3 fastest, then h2, h1, p6, p5, p4 (the reference's t3 element order)
+    coord[2] = (int) (r % p.ext[2]); r /= p.ext[2];
+    coord[1] = (int) (r % p.ext[1]); r /= p.ext[1];
+    coord[0] = (int) (r % p.ext[0]); r /= p.ext[0];
+    coord[5] = (int) (r % p.ext[5]); r /= p.ext[5];
+    coord[4] = (int) (r % p.ext[4]); r /= p.ext[4];
+    coord[3] = (int) r;
+    double d = 0.0;
+    for(int t = 0; t < p.nterms; t++) {
+      const TermDev& td = p.term[t];
+      const int      pl = td.pool;
+      const double*  A  = p.geom.hpp[pl] + td.hpp_panel * p.geom.hpp_stride_panel(pl) +
+                        coord[td.hpp_hole] * p.geom.hpp_stride_o2(pl) +
+                        coord[td.qt] * p.geom.hpp_stride_o1(pl) + coord[td.inner_hpp] * p.geom.hpp_stride_in(pl);
+      const double* B = p.geom.hhp[pl] + td.hhp_panel * p.geom.hhp_stride_panel(pl) +
+                        coord[td.hhp_o2] * p.geom.hhp_stride_o2(pl) +
+                        coord[td.hhp_o1] * p.geom.hhp_stride_o1(pl) + coord[td.inner_hhp] * p.geom.hhp_stride_in(pl);
+      const int nk = td.kslabs * KSLAB;
+      for(int k = 0; k < nk; k++) d = fma(A[k], B[k], d);
+    }
+    const double s = s1_sum(p, coord);
+    const double D = __ldg(p.evl[0] + coord[0]) + __ldg(p.evl[1] + coord[1]) + __ldg(p.evl[2] + coord[2]) -
+                     __ldg(p.evl[3] + coord[3]) - __ldg(p.evl[4] + coord[4]) - __ldg(p.evl[5] + coord[5]);
+    const double tmp = d / D;
+    e1 = tmp * d;
+    e2 = tmp * (d + s);
+  }
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1) {
+    e1 += __shfl_xor_sync(0xffffffffu, e1, o);
+    e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+  }
+  const int w = threadIdx.x >> 5;
+  if((threadIdx.x & 31) == 0) red[0][w] = e1, red[1][w] = e2;
+  __syncthreads();
+  if(threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for(int i = 0; i < 8; i++) a += red[0][i], b += red[1][i];
+    p.partial[2 * (int64_t) blockIdx.x]     = a;
+    p.partial[2 * (int64_t) blockIdx.x + 1] = b;
+  }
+}
+
+cudaError_t launch_fused_simple(const TaskParams& p, cudaStream_t st, int* grid_out) {
+  const int64_t total = (int64_t) p.ext[0] * p.ext[1] * p.ext[2] * p.ext[3] * p.ext[4] * p.ext[5];
+  const int     grid  = (int) ((total + 255) / 256);
+  if(grid_out) *grid_out = grid;
+  fused_t_simple_kernel<<<grid, 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// the fused DMMA kernel
+// =================================================================================================
+struct Ring {
+  uint32_t stage, phase;
+  __device__ __forceinline__ void advance(uint32_t nstages) {
+    if(++stage == nstages) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
+struct BoxCoord {
+  int off[6]; // element offset of the box inside the tile, per index id
+};
+
+__device__ __forceinline__ BoxCoord decode_box(const TaskParams& p, int box) {
+  // h3 fastest ... p4 slowest: consecutive (co-resident) boxes share most operand rows
+  BoxCoord b;
+  int      r = box;
+  int      q;
+  q = r % p.nbox[2]; r /= p.nbox[2]; b.off[2] = q * p.c[2];
+  q = r % p.nbox[1]; r /= p.nbox[1]; b.off[1] = q * p.c[1];
+  q = r % p.nbox[0]; r /= p.nbox[0]; b.off[0] = q * p.c[0];
+  q = r % p.nbox[5]; r /= p.nbox[5]; b.off[5] = q * PBOX;
+  q = r % p.nbox[4]; r /= p.nbox[4]; b.off[4] = q * PBOX;
+  b.off[3] = r * PBOX;
+  return b;
+}
+
+// All K slabs of one contraction for one consumer warp.
+// acc index = (((i1*2 + i2)*2 + i3)*2 + ql)*2 + r  with i* the hole offsets inside the warp group's
+// (2,2,2) sub-box, ql the warp's tile-particle slot and r the DMMA column parity.
+template<int HH, bool A_HPP>
+__device__ __forceinline__ void consume_term(double (&acc)[32], const TaskParams& p, const TermDev& td,
+                                             Ring& ring, uint32_t ring_base, uint32_t full_bar,
+                                             uint32_t empty_bar, const int sub_off[3], int wq, int lane) {
+  constexpr int HA = (HH == 0) ? 1 : 0;        // the two other holes, ascending
+  constexpr int HB = (HH == 2) ? 1 : 2;
+  const int     q  = lane >> 2, l3 = lane & 3;
+  // lane part of the swizzled fragment address (see DESIGN.md "shared-memory layout")
+  const uint32_t lane_const = (uint32_t) (q * ROW_BYTES + ((((l3 >> 1) ^ (q & 1)) << 4) | ((l3 & 1) << 3)));
+  const uint32_t jx         = (uint32_t) (q >> 1);
+
+  // row offsets (bytes) of this warp's 4 + 4 fragments inside a stage
+  const int hpp_rows = p.c[HH] * 64;
+  uint32_t  hpp_off[2][2], hhp_off[2][2];
+#pragma unroll
+  for(int ih = 0; ih < 2; ih++)
+#pragma unroll
+    for(int ql = 0; ql < 2; ql++)
+      hpp_off[ih][ql] = (uint32_t) ((((sub_off[HH] + ih) * 8 + 2 * wq + ql) * 8) * ROW_BYTES) + lane_const;
+  const int c_o1 = p.c[HB]; // HHP is [o2 = HA][o1 = HB][inner]
+#pragma unroll
+  for(int ia = 0; ia < 2; ia++)
+#pragma unroll
+    for(int ib = 0; ib < 2; ib++)
+      hhp_off[ia][ib] =
+        (uint32_t) ((hpp_rows + ((sub_off[HA] + ia) * c_o1 + sub_off[HB] + ib) * 8) * ROW_BYTES) + lane_const;
+
+  for(int s = 0; s < td.kslabs; s++) {
+    mbar_wait(full_bar + 8 * ring.stage, ring.phase, p.error_flag, 1);
+    const uint32_t base = ring_base + ring.stage * (uint32_t) p.stage_bytes;
+#pragma unroll
+    for(uint32_t j = 0; j < 4; j++) {
+      const uint32_t jo = base + ((j ^ jx) << 5);
+      double         fh[2][2], fg[2][2];
+#pragma unroll
+      for(int x = 0; x < 2; x++)
+#pragma unroll
+        for(int y = 0; y < 2; y++) {
+          fh[x][y] = lds_f64(jo + hpp_off[x][y]);
+          fg[x][y] = lds_f64(jo + hhp_off[x][y]);
+        }
+#pragma unroll
+      for(int i1 = 0; i1 < 2; i1++)
+#pragma unroll
+        for(int i2 = 0; i2 < 2; i2++)
+#pragma unroll
+          for(int i3 = 0; i3 < 2; i3++)
+#pragma unroll
+            for(int ql = 0; ql < 2; ql++) {
+              const int    hi[3] = {i1, i2, i3};
+              const double vh    = fh[hi[HH]][ql];
+              const double vg    = fg[hi[HA]][hi[HB]];
+              const int    ai    = ((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2);
+              if(A_HPP) dmma884(acc[ai], acc[ai + 1], vh, vg);
+              else dmma884(acc[ai], acc[ai + 1], vg, vh);
+            }
+    }
+    __syncwarp();
+    if(lane == 0) mbar_arrive(empty_bar + 8 * ring.stage);
+    ring.advance((uint32_t) p.stages);
+  }
+}
+
+__device__ __forceinline__ void consume_dispatch(double (&acc)[32], const TaskParams& p, const TermDev& td,
+                                                 Ring& ring, uint32_t ring_base, uint32_t full_bar,
+                                                 uint32_t empty_bar, const int sub_off[3], int wq, int lane) {
+  switch(td.hpp_hole * 2 + td.a_is_hpp) {
+    case 0: consume_term<0, false>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane); break;
+    case 1: consume_term<0, true>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane); break;
+    case 2: consume_term<1, false>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane); break;
+    case 3: consume_term<1, true>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane); break;
+    case 4: consume_term<2, false>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane); break;
+    default: consume_term<2, true>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane); break;
+  }
+}
+
+// producer: all slabs of one contraction for one box
+__device__ __forceinline__ void produce_term(const TaskParams& p, const TermDev& td, const BoxCoord& bc,
+                                             Ring& ring, uint32_t ring_base, uint32_t full_bar,
+                                             uint32_t empty_bar) {
+  const CUtensorMap* map_hpp = &p.tmap[td.pool * 2 + 0];
+  const CUtensorMap* map_hhp = &p.tmap[td.pool * 2 + 1];
+  const int          c_h     = p.c[td.hpp_hole];
+  const int          c_o2 = p.c[td.hhp_o2], c_o1 = p.c[td.hhp_o1];
+  const uint32_t     hpp_bytes = (uint32_t) (c_h * 64 * ROW_BYTES);
+  const uint32_t     tx        = hpp_bytes + (uint32_t) (c_o2 * c_o1 * 8 * ROW_BYTES);
+  const int          hpp_in = bc.off[td.inner_hpp], hpp_o1 = bc.off[td.qt];
+  const int          hpp_o2 = td.hpp_panel * p.geom.THp + bc.off[td.hpp_hole];
+  const int          hhp_in = bc.off[td.inner_hhp], hhp_o1 = bc.off[td.hhp_o1];
+  const int          hhp_o2 = td.hhp_panel * p.geom.THp + bc.off[td.hhp_o2];
+  for(int s = 0; s < td.kslabs; s++) {
+    mbar_wait(empty_bar + 8 * ring.stage, ring.phase ^ 1u, p.error_flag, 2);
+    const uint32_t bar = full_bar + 8 * ring.stage;
+    const uint32_t dst = ring_base + ring.stage * (uint32_t) p.stage_bytes;
+    mbar_arrive_expect_tx(bar, tx);
+    const int k0 = s * KSLAB;
+    for(int j = 0; j < c_h; j++)
+      tma_load_4d(dst + (uint32_t) (j * 64 * ROW_BYTES), map_hpp, bar, k0, hpp_in, hpp_o1, hpp_o2 + j);
+    for(int j2 = 0; j2 < c_o2; j2++)
+      for(int j1 = 0; j1 < c_o1; j1 += 2)
+        tma_load_4d(dst + hpp_bytes + (uint32_t) ((j2 * c_o1 + j1) * 8 * ROW_BYTES), map_hhp, bar, k0, hhp_in,
+                    hhp_o1 + j1, hhp_o2 + j2);
+    ring.advance((uint32_t) p.stages);
+  }
+}
+
+// blockDim.x = 32 * (consumer_warps + 1); the last warp is the TMA producer.
+// Two instantiations: <160,3> (4 consumer warps, three CTAs per SM) and <416,1> (8 or 12 consumer
+// warps, one CTA per SM); both get the full 128 registers per thread, which the 64 accumulator
+// registers + 16 fragment registers need to stay spill-free.
+template<int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_constant__ TaskParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES];
+  __shared__ double red[2][16];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncw = (int) (blockDim.x >> 5) - 1; // consumer warps
+
+  // 1024-byte aligned ring (the swizzle pattern is anchored on absolute smem address bits)
+  const uint32_t ring_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t full_bar  = smem_u32(&bars[0]);
+  const uint32_t empty_bar = smem_u32(&bars[MAX_STAGES]);
+
+  if(tid == 0) {
+    for(int s = 0; s < p.stages; s++) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, (uint32_t) ncw);
+    }
+    mbar_fence_init();
+  }
+  if(warp == ncw && lane == 0) {
+    for(int i = 0; i < 4; i++) tma_prefetch_desc(&p.tmap[i]);
+  }
+  __syncthreads();
+
+  const bool relayout = p.nterms_x > 0 && p.nterms_x < p.nterms;
+  Ring       ring{0u, 0u};
+
+  if(warp == ncw) {
+    // ================= producer warp =================
+    for(int box = blockIdx.x; box < p.nboxes; box += gridDim.x) {
+      const BoxCoord bc = decode_box(p, box);
+      if(lane == 0)
+        for(int t = 0; t < p.nterms_x; t++) produce_term(p, p.term[t], bc, ring, ring_base, full_bar, empty_bar);
+      __syncwarp(); // reconverge before the CTA-wide (aligned) barriers
+      if(relayout) {
+        __syncthreads(); // consumers are done with every X slab: the ring is idle
+        __syncthreads(); // accumulators parked in the ring
+        __syncthreads(); // accumulators reloaded: the ring may be refilled
+      }
+      if(lane == 0)
+        for(int t = p.nterms_x; t < p.nterms; t++) produce_term(p, p.term[t], bc, ring, ring_base, full_bar, empty_bar);
+      __syncwarp();
+    }
+    return;
+  }
+
+  // ================= consumer warps =================
+  const int grp = warp >> 2, wq = warp & 3;
+  int       sub_off[3];
+  {
+    const int g2 = grp % p.sub[2], g1 = (grp / p.sub[2]) % p.sub[1], g0 = grp / (p.sub[2] * p.sub[1]);
+    sub_off[0] = 2 * g0, sub_off[1] = 2 * g1, sub_off[2] = 2 * g2;
+  }
+  const int q6 = lane >> 2, l3 = lane & 3;
+
+  for(int box = blockIdx.x; box < p.nboxes; box += gridDim.x) {
+    const BoxCoord bc = decode_box(p, box);
+    double         acc[32];
+#pragma unroll
+    for(int i = 0; i < 32; i++) acc[i] = 0.0;
+
+    for(int t = 0; t < p.nterms_x; t++)
+      consume_dispatch(acc, p, p.term[t], ring, ring_base, full_bar, empty_bar, sub_off, wq, lane);
+
+    if(relayout) {
+      // X -> Y: swap the roles of p4 and p5 (tile particle <-> DMMA column) through shared memory.
+      // scratch index = ((((h1*c2 + h2)*c3 + h3)*8 + p4)*8 + p5)*8 + p6  (box-local coordinates)
+      __syncthreads();
+      double* scratch = reinterpret_cast<double*>(smem_raw + (ring_base - smem_u32(smem_raw)));
+#pragma unroll
+      for(int i1 = 0; i1 < 2; i1++)
+#pragma unroll
+        for(int i2 = 0; i2 < 2; i2++)
+#pragma unroll
+          for(int i3 = 0; i3 < 2; i3++)
+#pragma unroll
+            for(int ql = 0; ql < 2; ql++)
+#pragma unroll
+              for(int r = 0; r < 2; r++) {
+                const int hl = ((sub_off[0] + i1) * p.c[1] + sub_off[1] + i2) * p.c[2] + sub_off[2] + i3;
+                const int p4 = 2 * wq + ql, p5 = 2 * l3 + r;
+                scratch[((hl * 8 + p4) * 8 + p5) * 8 + q6] = acc[((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2) + r];
+              }
+      __syncthreads();
+#pragma unroll
+      for(int i1 = 0; i1 < 2; i1++)
+#pragma unroll
+        for(int i2 = 0; i2 < 2; i2++)
+#pragma unroll
+          for(int i3 = 0; i3 < 2; i3++)
+#pragma unroll
+            for(int ql = 0; ql < 2; ql++)
+#pragma unroll
+              for(int r = 0; r < 2; r++) {
+                const int hl = ((sub_off[0] + i1) * p.c[1] + sub_off[1] + i2) * p.c[2] + sub_off[2] + i3;
+                const int p5 = 2 * wq + ql, p4 = 2 * l3 + r;
+                acc[((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2) + r] = scratch[((hl * 8 + p4) * 8 + p5) * 8 + q6];
+              }
+      // generic-proxy accesses to the ring must be ordered before the TMA (async proxy) refills it
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+    }
+
+    for(int t = p.nterms_x; t < p.nterms; t++)
+      consume_dispatch(acc, p, p.term[t], ring, ring_base, full_bar, empty_bar, sub_off, wq, lane);
+
+    // ---------------- epilogue: s1, denominators, energy ----------------
+    const bool layout_y = p.nterms > p.nterms_x; // layout of the accumulators now
+    const int  id_qt = layout_y ? 4 : 3, id_qc = layout_y ? 3 : 4;
+    double     e1 = 0.0, e2 = 0.0;
+    const int  c6 = bc.off[5] + q6;
+    if(c6 < p.ext[5]) {
+      const double ep6 = __ldg(p.evl[5] + c6);
+#pragma unroll
+      for(int i1 = 0; i1 < 2; i1++)
+#pragma unroll
+        for(int i2 = 0; i2 < 2; i2++)
+#pragma unroll
+          for(int i3 = 0; i3 < 2; i3++)
+#pragma unroll
+            for(int ql = 0; ql < 2; ql++)
+#pragma unroll
+              for(int r = 0; r < 2; r++) {
+                int coord[6];
+                coord[0]     = bc.off[0] + sub_off[0] + i1;
+                coord[1]     = bc.off[1] + sub_off[1] + i2;
+                coord[2]     = bc.off[2] + sub_off[2] + i3;
+                coord[id_qt] = bc.off[id_qt] + 2 * wq + ql;
+                coord[id_qc] = bc.off[id_qc] + 2 * l3 + r;
+                coord[5]     = c6;
+                if(coord[0] < p.ext[0] && coord[1] < p.ext[1] && coord[2] < p.ext[2] && coord[3] < p.ext[3] &&
+                   coord[4] < p.ext[4]) {
+                  const double d = acc[((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2) + r];
+                  const double s = s1_sum(p, coord);
+                  const double D = __ldg(p.evl[0] + coord[0]) + __ldg(p.evl[1] + coord[1]) +
+                                   __ldg(p.evl[2] + coord[2]) - __ldg(p.evl[3] + coord[3]) -
+                                   __ldg(p.evl[4] + coord[4]) - ep6;
+                  const double tmp = d / D;
+                  e1 += tmp * d;
+                  e2 += tmp * (d + s);
+                }
+              }
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) {
+      e1 += __shfl_xor_sync(0xffffffffu, e1, o);
+      e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+    }
+    if(lane == 0) red[0][warp] = e1, red[1][warp] = e2;
+    named_bar_sync(1, ncw * 32);
+    if(tid == 0) {
+      double a = 0.0, b = 0.0;
+      for(int i = 0; i < ncw; i++) a += red[0][i], b += red[1][i];
+      p.partial[2 * (int64_t) box]     = a;
+      p.partial[2 * (int64_t) box + 1] = b;
+    }
+    named_bar_sync(1, ncw * 32); // red[] may be overwritten by the next box
+  }
+}
+
+cudaError_t fused_dmma_configure(size_t smem_bytes) {
+  cudaError_t e = cudaFuncSetAttribute(fused_t_dmma_kernel<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int) smem_bytes);
+  if(e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(fused_t_dmma_kernel<416, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int) smem_bytes);
+}
+
+int fused_dmma_max_ctas_per_sm(int threads, size_t smem_bytes) {
+  int         n = 0;
+  cudaError_t e = threads <= 160
+                    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_t_dmma_kernel<160, 3>, threads, smem_bytes)
+                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_t_dmma_kernel<416, 1>, threads, smem_bytes);
+  return e == cudaSuccess ? n : 0;
+}
+
+cudaError_t launch_fused_dmma(const TaskParams& p, int grid, int consumer_warps, size_t smem_bytes,
+                              cudaStream_t st) {
+  const int threads = 32 * (consumer_warps + 1);
+  if(threads <= 160) fused_t_dmma_kernel<160, 3><<<grid, threads, smem_bytes, st>>>(p);
+  else if(threads <= 416) fused_t_dmma_kernel<416, 1><<<grid, threads, smem_bytes, st>>>(p);
+  else return cudaErrorInvalidConfiguration;
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// fixed-order reduction of per-box partials: out2[0..1] = sum(partial[:,0]), sum(partial[:,1])
+// =================================================================================================
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partial, int n,
+                                                              double* __restrict__ out2) {
+  __shared__ double sh[2][256];
+  double            a = 0.0, b = 0.0;
+  for(int i = threadIdx.x; i < n; i += 256) {
+    a += partial[2 * (int64_t) i];
+    b += partial[2 * (int64_t) i + 1];
+  }
+  sh[0][threadIdx.x] = a;
+  sh[1][threadIdx.x] = b;
+  __syncthreads();
+  for(int s = 128; s > 0; s >>= 1) {
+    if((int) threadIdx.x < s) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if(threadIdx.x == 0) out2[0] = sh[0][0], out2[1] = sh[1][0];
+}
+
+cudaError_t launch_reduce_partials(const double* partial, int n, double* out2, cudaStream_t st) {
+  reduce_partials_kernel<<<1, 256, 0, st>>>(partial, n, out2);
+  return cudaGetLastError();
+}
+
+// =================================================================================================
+// probes
+// =================================================================================================
+__global__ void __launch_bounds__(256) fp64_fma_peak_kernel(double* out, int iters, double x) {
+  double a[16];
+#pragma unroll
+  for(int i = 0; i < 16; i++) a[i] = threadIdx.x * 1e-9 + i;
+  const double b = x, c = 1.0 - x * 1e-3;
+  for(int it = 0; it < iters; it++) {
+#pragma unroll
+    for(int i = 0; i < 16; i++) a[i] = fma(a[i], c, b);
+  }
+  double s = 0;
+#pragma unroll
+  for(int i = 0; i < 16; i++) s += a[i];
+  out[(int64_t) blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) fp64_dmma_peak_kernel(double* out, int iters, double x) {
+  double acc[32];
+#pragma unroll
+  for(int i = 0; i < 32; i++) acc[i] = 0.0;
+  const double a = x + threadIdx.x * 1e-9, b = 1.0 - x * 1e-3;
+  for(int it = 0; it < iters; it++) {
+#pragma unroll
+    for(int i = 0; i < 16; i++) dmma884(acc[2 * i], acc[2 * i + 1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for(int i = 0; i < 32; i++) s += acc[i];
+  out[(int64_t) blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+cudaError_t probe_fp64_peak(int use_dmma, int iters, double* tflops, double* ms_out) {
+  cudaDeviceProp prop;
+  int            dev = 0;
+  cudaGetDevice(&dev);
+  cudaError_t err = cudaGetDeviceProperties(&prop, dev);
+  if(err != cudaSuccess) return err;
+  const int grid = prop.multiProcessorCount * 8, block = 256;
+  double*   out  = nullptr;
+  if((err = cudaMalloc(&out, sizeof(double) * grid * block)) != cudaSuccess) return err;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for(int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0);
+    if(use_dmma) fp64_dmma_peak_kernel<<<grid, block>>>(out, iters, 0.5);
+    else fp64_fma_peak_kernel<<<grid, block>>>(out, iters, 0.5);
+    cudaEventRecord(e1);
+    if((err = cudaEventSynchronize(e1)) != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if(rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if(err != cudaSuccess) return err;
+  const double flops = use_dmma ? (double) grid * (block / 32) * (double) iters * 16.0 * 512.0
+                                : (double) grid * block * (double) iters * 16.0 * 2.0;
+  *ms_out            = best;
+  *tflops            = flops / (best * 1e-3) / 1e12;
+  return cudaGetLastError();
+}
+
+__global__ void dmma_layout_kernel(double* c_out, const double* a, const double* b) {
+  const int lane = threadIdx.x;
+  double    d0 = 0.0, d1 = 0.0;
+  dmma884(d0, d1, a[(lane >> 2) * 4 + (lane & 3)], b[(lane & 3) * 8 + (lane >> 2)]);
+  c_out[(lane >> 2) * 8 + 2 * (lane & 3)]     = d0;
+  c_out[(lane >> 2) * 8 + 2 * (lane & 3) + 1] = d1;
+}
+
+cudaError_t probe_dmma_layout(double* c_host, const double* a_host, const double* b_host) {
+  double *    a, *b, *c;
+  cudaError_t err;
+  if((err = cudaMalloc(&a, 32 * 8)) != cudaSuccess) return err;
+  cudaMalloc(&b, 32 * 8);
+  cudaMalloc(&c, 64 * 8);
+  cudaMemcpy(a, a_host, 32 * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(b, b_host, 32 * 8, cudaMemcpyHostToDevice);
+  dmma_layout_kernel<<<1, 32>>>(c, a, b);
+  err = cudaMemcpy(c_host, c, 64 * 8, cudaMemcpyDeviceToHost);
+  cudaFree(a), cudaFree(b), cudaFree(c);
+  return err;
+}
+
+// loads `rows` rows x 16 doubles of a [rows/8][8][16] tensor holding value = row*16 + k through a
+// (16,8,2,1)-box / 128B-swizzle tensor map and dumps shared memory verbatim
+__global__ void tma_swizzle_kernel(const __grid_constant__ CUtensorMap map, double* dump, int rows,
+                                   uint32_t* error_flag) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b    = smem_u32(&bar);
+  if(threadIdx.x == 0) {
+    mbar_init(b, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if(threadIdx.x == 0) {
+    mbar_arrive_expect_tx(b, (uint32_t) (rows * ROW_BYTES));
+    for(int r = 0; r < rows; r += 16) tma_load_4d(base + (uint32_t) (r * ROW_BYTES), &map, b, 0, 0, r / 8, 0);
+  }
+  mbar_wait(b, 0, error_flag, 3);
+  const double* s = reinterpret_cast<const double*>(smem_raw + (base - smem_u32(smem_raw)));
+  for(int i = threadIdx.x; i < rows * 16; i += blockDim.x) dump[i] = s[i];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+cudaError_t probe_tma_swizzle(double* dump_host, int rows) {
+  if(rows % 16 || rows <= 0 || rows > 512) return cudaErrorInvalidValue;
+  void*                           fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if(err != cudaSuccess || !fn) return err != cudaSuccess ? err : cudaErrorUnknown;
+  double *src, *dump;
+  uint32_t* flag;
+  cudaMalloc(&src, (size_t) rows * 16 * 8);
+  cudaMalloc(&dump, (size_t) rows * 16 * 8);
+  cudaMalloc(&flag, 4);
+  cudaMemset(flag, 0, 4);
+  double* h = (double*) malloc((size_t) rows * 16 * 8);
+  for(int i = 0; i < rows * 16; i++) h[i] = (double) i;
+  cudaMemcpy(src, h, (size_t) rows * 16 * 8, cudaMemcpyHostToDevice);
+  free(h);
+  CUtensorMap map;
+  cuuint64_t  dims[4]    = {16, 8, (cuuint64_t) (rows / 8), 1};
+  cuuint64_t  strides[3] = {128, 1024, (cuuint64_t) rows * 128};
+  cuuint32_t  box[4]     = {16, 8, 2, 1};
+  cuuint32_t  es[4]      = {1, 1, 1, 1};
+  CUresult    r = ((EncodeTiledFn) fn)(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, src, dims, strides, box, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if(r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  const size_t smem = (size_t) rows * ROW_BYTES + 1024;
+  cudaFuncSetAttribute(tma_swizzle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  tma_swizzle_kernel<<<1, 128, smem>>>(map, dump, rows, flag);
+  err = cudaMemcpy(dump_host, dump, (size_t) rows * 16 * 8, cudaMemcpyDeviceToHost);
+  cudaFree(src), cudaFree(dump), cudaFree(flag);
+  return err;
+}
+
+__global__ void synth_block_kernel(SynthInfo si, int tensor, int64_t l0, int64_t l1, int64_t l2, int64_t l3,
+                                   int64_t n0, int64_t n1, int64_t n2, int64_t n3, double* out) {
+  const int64_t total = n0 * n1 * n2 * n3;
+  for(int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+    int64_t r = e;
+    int64_t idx[4];
+    idx[3] = l3 + r % n3; r /= n3;
+    idx[2] = l2 + r % n2; r /= n2;
+    idx[1] = l1 + r % n1; r /= n1;
+    idx[0] = l0 + r;
+    out[e] = synth_value(si, tensor, idx);
+  }
+}
+
+cudaError_t synth_block_device(SynthInfo si, int tensor, const int64_t lo[4], const int64_t n[4], double* host_out) {
+  const int64_t total = n[0] * n[1] * n[2] * n[3];
+  double*       d;
+  cudaError_t   err = cudaMalloc(&d, (size_t) total * 8);
+  if(err != cudaSuccess) return err;
+  synth_block_kernel<<<(unsigned) ((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256), 256>>>(
+    si, tensor, lo[0], lo[1], lo[2], lo[3], n[0], n[1], n[2], n[3], d);
+  err = cudaMemcpy(host_out, d, (size_t) total * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return err;
+}
+
+} // namespace ccsdt

@@ -1,0 +1,140 @@
+/*
+ * ccsdt_b200.h -- C ABI of the B200-native fused CCSD(T) triples driver.
+ *
+ * Drop-in boundary for ExaChem's (T) hot path.  Each entry point names the reference interface it
+ * replaces (paths relative to the ExaChem source tree):
+ *
+ *   ccsdt_set_space      <- MO("occ"/"virt"/"occ_alpha"/"virt_alpha").num_tiles(), MO.input_tile_sizes(),
+ *                           k_spin, k_evl_sorted, is_restricted arguments of
+ *                           CCSD_T_Fused_Driver<T>::execute  exachem/cc/ccsd_t/ccsd_t_fused_driver.hpp:73-81,112-126
+ *   ccsdt_tiles          <- Cholesky_2E_Util::setupMOIS(ec, chem_env, triples=true)
+ *                           exachem/cholesky/cholesky_2e.cpp:186-190,230-279 and k_spin of
+ *                           exachem/cc/ccsd_t/ccsd_t.cpp:245-249
+ *   ccsdt_enumerate      <- the task loops of execute        ccsd_t_fused_driver.hpp:368-395,478
+ *   ccsdt_task_terms     <- ccsd_t_data_{s1,d1,d2}_info_only ccsd_t_all_fused_{singles,doubles1,doubles2}.hpp
+ *   ccsdt_count_ops      <- calculate_performance_ops        ccsd_t_fused_driver.hpp:83-87,548-638
+ *                           (+ helper_calculate_num_ops      fused_common.hpp:131-261)
+ *   ccsdt_put_dense / ccsdt_put_block / ccsdt_set_fetch
+ *                        <- Tensor<T>::get on d_t1, d_t2, d_v2.{v2ijab,v2ijka,v2iabc}
+ *                           ccsd_t_all_fused_singles.hpp:200,304; ..._doubles1.hpp:222,237,282;
+ *                           ..._doubles2.hpp:215,230,335  (and the six LRUCache arguments: the HBM block
+ *                           store replaces them)
+ *   ccsdt_run            <- execute's task loop + ccsd_t_fully_fused_none_df_none_task
+ *                           ccsd_t_all_fused.hpp:77-286 + the kernel launcher ccsd_t_all_fused_gpu.cu:2571
+ *                           + hostEnergyReduce ccsd_t_all_fused.hpp:19-32; returns the rank-partial
+ *                           (energy1 = E[T], energy2 = E(T)) the caller reduces at ccsd_t.cpp:262-263
+ *   ccsdt_check_memory   <- check_memory_req                 exachem/cc/ccsd_t/hybrid.cpp:19-41
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types.  Every function returns 0 on success
+ * and a non-zero code on failure; ccsdt_last_error() gives the message.  (The reference's convention
+ * is fatal: CUDA_SAFE -> exit(100), ccsd_t_common.hpp:26-31; the C++ adapter in
+ * include/ccsd_t_fused_driver_b200.hpp turns non-zero into tamm_terminate.)  There is no CPU
+ * fallback: ccsdt_create fails when no CUDA device is usable.
+ *
+ * A context is single-caller (one host thread), bound to one GPU.  One process per GPU; rank /
+ * nranks in ccsdt_options select this process's share of the task list.
+ */
+#ifndef CCSDT_B200_H
+#define CCSDT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CCSDT_API __attribute__((visibility("default")))
+#else
+#define CCSDT_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ccsdt_ctx ccsdt_ctx;
+
+/* tensor ids; block ids are tile indices inside the tensor's own sub-space, exactly what the
+ * reference passes to Tensor::get (a virtual tile p is passed as p - noab) */
+enum {
+  CCSDT_T1     = 0, /* d_t1   [V][O]          */
+  CCSDT_T2     = 1, /* d_t2   [V][V][O][O]    */
+  CCSDT_V_IJAB = 2, /* v2ijab [O][O][V][V]    */
+  CCSDT_V_IJKA = 3, /* v2ijka [O][O][O][V]    */
+  CCSDT_V_IABC = 4  /* v2iabc [O][V][V][V]    */
+};
+
+enum { CCSDT_KERNEL_DMMA = 0, CCSDT_KERNEL_SIMPLE = 1 };
+
+typedef struct ccsdt_options {
+  int32_t kernel;        /* CCSDT_KERNEL_DMMA (product) or CCSDT_KERNEL_SIMPLE (diagnostic FMA kernel) */
+  int32_t sub[3];        /* CTA box = (2*sub[0], 2*sub[1], 2*sub[2], 8, 8, 8) over (h1,h2,h3,p4,p5,p6);
+                            each entry 1..3, product <= 3 (4, 8 or 12 DMMA warps + 1 TMA warp).  0 = default (1,1,2) */
+  int32_t stages;        /* TMA ring depth, 0 = as many as fit */
+  int32_t ctas_per_sm;   /* 0 = default for the box */
+  int32_t rank, nranks;  /* this process's share of the task list (static cost-balanced split) */
+  int32_t overlap;       /* 1 = stage task n+1 while task n computes (default), 0 = serial */
+  int32_t verbose;
+} ccsdt_options;
+
+typedef struct ccsdt_stats {
+  int64_t tasks_run;          /* kernel tasks executed by this rank */
+  int64_t kernel_launches;    /* launches of this library's kernels */
+  double  counted_flops;      /* total_num_ops share of the tasks run (reference's count) */
+  double  seconds_total;      /* wall time of ccsdt_run */
+  double  seconds_kernel;     /* CUDA-event time of the fused kernel launches (sum) */
+  double  seconds_staging;    /* CUDA-event time of the panel-build launches (sum) */
+  int64_t h2d_bytes, d2h_bytes;
+  int64_t blocks_fetched;     /* fetch-callback invocations */
+} ccsdt_stats;
+
+/* delivers one UNSORTED row-major block, i.e. what Tensor<T>::get(bid, buf) returns */
+typedef int (*ccsdt_fetch_fn)(void* user, int tensor, const uint32_t bid[4], double* dst, size_t n);
+
+CCSDT_API int         ccsdt_create(ccsdt_ctx** out, int device);
+CCSDT_API int         ccsdt_destroy(ccsdt_ctx* ctx);
+CCSDT_API const char* ccsdt_last_error(const ccsdt_ctx* ctx); /* ctx may be NULL: error of the last failed create */
+CCSDT_API int         ccsdt_default_options(ccsdt_options* opt);
+CCSDT_API int         ccsdt_set_options(ccsdt_ctx* ctx, const ccsdt_options* opt);
+
+/* host-only helpers (no GPU needed; ctx-free) */
+CCSDT_API int     ccsdt_tiles(int64_t n_occ_alpha, int64_t n_occ_beta, int64_t n_vir_alpha, int64_t n_vir_beta,
+                    int64_t tilesize, int64_t* k_range, int32_t* k_spin, int32_t counts[4], int cap);
+CCSDT_API int64_t ccsdt_enumerate(int noab, int nvab, const int32_t* k_spin, int is_restricted, int64_t* tasks7,
+                        double* factors, int64_t cap, int64_t* n_outer);
+CCSDT_API int     ccsdt_task_terms(int noab, int nvab, const int32_t* k_spin, const int64_t* k_range,
+                         int is_restricted, const int64_t task[6], uint8_t* s1_on /*9*/,
+                         uint8_t* d1_on /*9*noab*/, uint8_t* d2_on /*9*nvab*/);
+CCSDT_API int     ccsdt_count_ops(int noab, int nvab, const int32_t* k_spin, const int64_t* k_range,
+                        int is_restricted, long double* total_num_ops);
+CCSDT_API int     ccsdt_partition(int noab, int nvab, const int32_t* k_spin, const int64_t* k_range,
+                        int is_restricted, int nranks, int32_t* owner /* one per kernel task */,
+                        int64_t cap);
+CCSDT_API int     ccsdt_check_memory(int tilesize, int nbf, size_t gpu_bytes, size_t* required);
+
+/* problem definition */
+CCSDT_API int ccsdt_set_space(ccsdt_ctx* ctx, int noa, int nob, int nva, int nvb, const int64_t* k_range,
+                    const int32_t* k_spin, const double* evl, int is_restricted);
+
+/* operand supply (choose one per tensor) */
+CCSDT_API int ccsdt_put_dense(ccsdt_ctx* ctx, int tensor, const double* host_dense);
+CCSDT_API int ccsdt_put_block(ccsdt_ctx* ctx, int tensor, const uint32_t bid[4], const double* host_block);
+CCSDT_API int ccsdt_set_fetch(ccsdt_ctx* ctx, ccsdt_fetch_fn fn, void* user);
+CCSDT_API int ccsdt_set_synthetic(ccsdt_ctx* ctx, uint64_t seed); /* procedural tensors generated on the device */
+
+/* runs kernel tasks [task_begin, task_end) of the canonical list that belong to this rank
+ * (task_end < 0 = to the end).  energies[0] = E[T] partial, energies[1] = E(T) partial, both already
+ * weighted by the task factors and summed in task order.  per_task (optional) receives 2 doubles
+ * per task of the range (zeros for tasks owned by other ranks). */
+CCSDT_API int ccsdt_run(ccsdt_ctx* ctx, int64_t task_begin, int64_t task_end, double energies[2],
+              double* per_task, ccsdt_stats* stats);
+
+/* diagnostics used by tests and bench (device microbenchmarks and unit probes) */
+CCSDT_API int ccsdt_probe_fp64_peak(int device, int use_dmma, int iters, double* tflops, double* ms);
+CCSDT_API int ccsdt_probe_dmma_layout(int device, double* c_out /*64*/, const double* a /*8x4*/, const double* b /*4x8*/);
+CCSDT_API int ccsdt_probe_tma_swizzle(int device, double* smem_dump /*rows*16*/, int rows);
+CCSDT_API int ccsdt_synth_block(int device, uint64_t seed, int tensor, int noa, int nob, int nva, int nvb,
+                      const int64_t lo[4], const int64_t n[4], double* host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCSDT_B200_H */

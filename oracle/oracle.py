@@ -155,6 +155,9 @@ class Reference:
         L.ref_ccsdt_count_ops.argtypes = [C.c_int] * 4 + [_i64p, _i32p, C.c_int, C.POINTER(C.c_longdouble)]
         L.ref_ccsdt_task_info.argtypes = [C.c_int] * 4 + [_i64p, _i32p, C.c_int] + [C.c_int] * 6 + [_i32p] * 4
         L.ref_ccsdt_num_threads.restype = C.c_int
+        L.ref_ccsdt_execute_synth.argtypes = [C.c_int] * 4 + [_i64p, _i32p, _dp, _i64p, C.c_uint64, C.c_int,
+                                                               C.c_int, C.c_int, C.c_int64, _dp, _i64p]
+        L.ref_ccsdt_execute_synth.restype = C.c_int
         self.L = L
 
     def num_threads(self) -> int:
@@ -175,6 +178,20 @@ class Reference:
                                  1 if enumerate_only else 0, task_limit, _p(out, _dp), _p(trace, _dp), cap,
                                  C.byref(n))
         return out, trace[:min(n.value, cap)].copy()
+
+    def execute_synth(self, sp: Space, evl, n_orb, seed: int, is_restricted: bool, tilesize=40,
+                      cache_size=8, task_limit=-1):
+        """reference `execute` on procedural tensors; computes only the first task_limit kernel tasks"""
+        ks = np.ascontiguousarray(sp.k_spin, np.int32)
+        kr = np.ascontiguousarray(sp.k_range, np.int64)
+        ev = np.ascontiguousarray(evl, np.float64)
+        no = np.ascontiguousarray(n_orb, np.int64)
+        out = np.zeros(4)
+        n = C.c_int64(0)
+        self.L.ref_ccsdt_execute_synth(sp.noa, sp.nob, sp.nva, sp.nvb, _p(kr, _i64p), _p(ks, _i32p), _p(ev, _dp),
+                                       _p(no, _i64p), seed, int(is_restricted), tilesize, cache_size, task_limit,
+                                       _p(out, _dp), C.byref(n))
+        return out, int(n.value)
 
     def count_ops(self, sp: Space, is_restricted: bool) -> int:
         ks = np.ascontiguousarray(sp.k_spin, np.int32)

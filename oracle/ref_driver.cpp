@@ -265,3 +265,112 @@ int ref_ccsdt_num_threads() {
 }
 
 } // extern "C"
+
+// ---- procedural tensors (same counter-based generator as exachem_b200/synthetic.py) so that the
+//      reference can be timed on shapes whose dense tensors would not fit in host memory ----------
+namespace {
+inline uint64_t synth_mix(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+inline double synth_raw(uint64_t seed, int tensor, int64_t i0, int64_t i1, int64_t i2, int64_t i3) {
+  static const double scale[5] = {0.05, 0.1, 0.1, 0.1, 0.1};
+  uint64_t key = ((uint64_t) i0 << 48) | ((uint64_t) i1 << 32) | ((uint64_t) i2 << 16) | (uint64_t) i3;
+  uint64_t s   = synth_mix(seed ^ ((uint64_t) (tensor + 1) * 0xD1B54A32D192ED03ull));
+  uint64_t h   = synth_mix(s ^ key);
+  double   u   = (double) (h >> 11) * (1.0 / 9007199254740992.0);
+  return (2.0 * u - 1.0) * scale[tensor];
+}
+struct SynthOrb {
+  uint64_t seed;
+  int64_t  noa, nob, nva, nvb;
+  int so(int64_t i) const { return i < noa ? 1 : 2; }
+  int sv(int64_t a) const { return a < nva ? 1 : 2; }
+  double value(int tensor, int64_t a, int64_t b, int64_t c, int64_t d) const {
+    double sign = 1.0;
+    switch(tensor) {
+      case 0: return sv(a) == so(b) ? synth_raw(seed, 0, a, b, 0, 0) : 0.0;
+      case 1:
+        if(a == b || c == d || sv(a) + sv(b) != so(c) + so(d)) return 0.0;
+        if(a > b) std::swap(a, b), sign = -sign;
+        if(c > d) std::swap(c, d), sign = -sign;
+        return sign * synth_raw(seed, 1, a, b, c, d);
+      case 2:
+        if(a == b || c == d || so(a) + so(b) != sv(c) + sv(d)) return 0.0;
+        if(a > b) std::swap(a, b), sign = -sign;
+        if(c > d) std::swap(c, d), sign = -sign;
+        return sign * synth_raw(seed, 2, a, b, c, d);
+      case 3:
+        if(a == b || so(a) + so(b) != so(c) + sv(d)) return 0.0;
+        if(a > b) std::swap(a, b), sign = -sign;
+        return sign * synth_raw(seed, 3, a, b, c, d);
+      default:
+        if(c == d || so(a) + sv(b) != sv(c) + sv(d)) return 0.0;
+        if(c > d) std::swap(c, d), sign = -sign;
+        return sign * synth_raw(seed, 4, a, b, c, d);
+    }
+  }
+};
+
+Tensor<double> synth_tensor(const Space& s, const SynthOrb& orb, int tensor, std::string kinds) {
+  return Tensor<double>([&s, orb, tensor, kinds](const IndexVector& bid, std::vector<double>& buf) {
+    const int d = (int) kinds.size();
+    int64_t   ext[4] = {1, 1, 1, 1}, off[4] = {0, 0, 0, 0};
+    for(int i = 0; i < d; i++) {
+      size_t tile = kinds[i] == 'o' ? bid[i] : bid[i] + s.noab;
+      ext[i]      = (int64_t) s.k_range[tile];
+      off[i]      = (int64_t) (s.k_offset[tile] - (kinds[i] == 'o' ? 0 : s.Ot));
+    }
+    size_t n = (size_t) (ext[0] * ext[1] * ext[2] * ext[3]);
+    if(buf.size() < n) buf.resize(n);
+    size_t lin = 0;
+    for(int64_t a = 0; a < ext[0]; a++)
+      for(int64_t b = 0; b < ext[1]; b++)
+        for(int64_t c = 0; c < ext[2]; c++)
+          for(int64_t e = 0; e < ext[3]; e++)
+            buf[lin++] = orb.value(tensor, off[0] + a, off[1] + b, d > 2 ? off[2] + c : 0, d > 3 ? off[3] + e : 0);
+  });
+}
+} // namespace
+
+extern "C" {
+// Same as ref_ccsdt_execute but on procedural tensors: n_orb = orbital counts (occ a, occ b, virt a,
+// virt b) the generator needs for the spin of an index.  Used by bench.py for the CPU baseline.
+int ref_ccsdt_execute_synth(int noa, int nob, int nva, int nvb, const int64_t* k_range,
+                            const int32_t* k_spin, const double* evl, const int64_t* n_orb, uint64_t seed,
+                            int is_restricted, int tilesize, int cache_size, int64_t task_limit,
+                            double* out, int64_t* n_trace) {
+  Space            s  = make_space(noa, nob, nva, nvb, k_range, k_spin);
+  TiledIndexSpace  MO = make_mo(s, noa, nob, nva, nvb);
+  ExecutionContext ec;
+  ChemEnv          chem_env;
+  chem_env.ioptions.ccsd_options.ccsdt_tilesize = tilesize;
+  SynthOrb orb{seed, n_orb[0], n_orb[1], n_orb[2], n_orb[3]};
+  Tensor<double>                          d_t1 = synth_tensor(s, orb, 0, "vo");
+  Tensor<double>                          d_t2 = synth_tensor(s, orb, 1, "vvoo");
+  exachem::cholesky_2e::V2Tensors<double> d_v2;
+  d_v2.v2ijab = synth_tensor(s, orb, 2, "oovv");
+  d_v2.v2ijka = synth_tensor(s, orb, 3, "ooov");
+  d_v2.v2iabc = synth_tensor(s, orb, 4, "ovvv");
+  std::vector<double>                  k_evl(evl, evl + s.Ot + s.Vt);
+  LRUCache<Index, std::vector<double>> cache_s1t{(size_t) cache_size}, cache_s1v{(size_t) cache_size};
+  LRUCache<Index, std::vector<double>> cache_d1t{(size_t) cache_size * s.noab}, cache_d1v{(size_t) cache_size * s.noab};
+  LRUCache<Index, std::vector<double>> cache_d2t{(size_t) cache_size * s.nvab}, cache_d2v{(size_t) cache_size * s.nvab};
+  g_trace.clear();
+  g_trace_skip_compute = 0;
+  g_trace_limit        = task_limit;
+  CCSD_T_Fused_Driver<double> drv;
+  double                      e1, e2, tw, tt;
+  {
+    Silence quiet;
+    std::tie(e1, e2, tw, tt) = drv.execute(chem_env, ec, s.k_spin, MO, d_t1, d_t2, d_v2, k_evl, 0.0,
+                                           is_restricted != 0, cache_s1t, cache_s1v, cache_d1t, cache_d1v,
+                                           cache_d2t, cache_d2v, true);
+  }
+  out[0] = e1, out[1] = e2, out[2] = tw, out[3] = tt;
+  if(n_trace) *n_trace = (int64_t) g_trace.size();
+  return 0;
+}
+}
