@@ -422,6 +422,7 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     TermDev td{};
     td.pool      = 0;
     td.kslabs    = (int) ((K + KSLAB - 1) / KSLAB);
+    td.ksteps_last = (int) ((K - (int64_t) (td.kslabs - 1) * KSLAB + 3) / 4);
     td.hpp_hole  = T.hx;
     td.qt        = T.pa;
     td.inner_hpp = T.pb;
@@ -487,6 +488,7 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     TermDev td{};
     td.pool      = 1;
     td.kslabs    = (int) ((K + KSLAB - 1) / KSLAB);
+    td.ksteps_last = (int) ((K - (int64_t) (td.kslabs - 1) * KSLAB + 3) / 4);
     td.hpp_hole  = T.hz;
     td.qt        = T.pb;
     td.inner_hpp = T.pc;
@@ -1007,6 +1009,12 @@ static int probe_device(int device) {
 int ccsdt_probe_fp64_peak(int device, int use_dmma, int iters, double* tflops, double* ms) {
   if(int rc = probe_device(device)) return rc;
   cudaError_t e = probe_fp64_peak(use_dmma, iters, tflops, ms);
+  if(e != cudaSuccess) g_create_error = cudaGetErrorString(e);
+  return e == cudaSuccess ? 0 : 2;
+}
+int ccsdt_probe_mainloop(int device, int ta, int tb, int warps_per_cta, int ctas_per_sm, int iters, double* tflops) {
+  if(int rc = probe_device(device)) return rc;
+  cudaError_t e = probe_mainloop(ta, tb, warps_per_cta, ctas_per_sm, iters, tflops);
   if(e != cudaSuccess) g_create_error = cudaGetErrorString(e);
   return e == cudaSuccess ? 0 : 2;
 }

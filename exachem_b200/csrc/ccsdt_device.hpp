@@ -43,6 +43,7 @@ struct PoolGeom {
 struct TermDev {
   int32_t pool;      // 0 = d1, 1 = d2
   int32_t kslabs;    // number of KSLAB-wide slabs
+  int32_t ksteps_last; // 4-wide DMMA k-steps of the last slab (1..4): K is padded to 4, not 16, in compute
   int32_t layout_y;  // 0 = X, 1 = Y
   int32_t a_is_hpp;  // 1: HPP is the a-side, 0: HHP is
   int32_t hpp_hole;  // hole index (0..2) of HPP dim o2
@@ -106,6 +107,7 @@ cudaError_t fused_dmma_configure(size_t smem_bytes);
 int         fused_dmma_max_ctas_per_sm(int threads, size_t smem_bytes);
 
 cudaError_t probe_fp64_peak(int use_dmma, int iters, double* tflops, double* ms);
+cudaError_t probe_mainloop(int ta, int tb, int warps_per_cta, int ctas_per_sm, int iters, double* tflops);
 cudaError_t probe_dmma_layout(double* c_out, const double* a, const double* b);
 cudaError_t probe_tma_swizzle(double* smem_dump, int rows);
 cudaError_t synth_block_device(SynthInfo si, int tensor, const int64_t lo[4], const int64_t n[4],

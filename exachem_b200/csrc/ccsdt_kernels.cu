@@ -210,6 +210,12 @@ cudaError_t launch_fused_simple(const TaskParams& p, cudaStream_t st, int* grid_
 // =================================================================================================
 // the fused DMMA kernel
 // =================================================================================================
+// Fragment row r (0..7) of an 8-row operand group is stored in shared-memory row 2*(r&3) + (r>>2).
+// With the TMA 128-byte swizzle (16-byte chunk ^= row & 7) this makes every 64-bit fragment load
+// conflict-free per half-warp; the natural order has a 2-way conflict (rows 0-3 only reach 4 of the
+// 8 chunks).  Consequence: DMMA row r / column n correspond to particle offsets frag_row(r) / frag_row(n).
+__device__ __forceinline__ int frag_row(int r) { return 2 * (r & 3) + (r >> 2); }
+
 struct Ring {
   uint32_t stage, phase;
   __device__ __forceinline__ void advance(uint32_t nstages) {
@@ -247,8 +253,10 @@ __device__ __forceinline__ void consume_term(double (&acc)[32], const TaskParams
                                              uint32_t empty_bar, const int sub_off[3], int wq, int lane) {
   constexpr int HA = (HH == 0) ? 1 : 0;        // the two other holes, ascending
   constexpr int HB = (HH == 2) ? 1 : 2;
-  const int     q  = lane >> 2, l3 = lane & 3;
-  // lane part of the swizzled fragment address (see DESIGN.md "shared-memory layout")
+  const int     q  = frag_row(lane >> 2), l3 = lane & 3;
+  // lane part of the swizzled fragment address (see DESIGN.md "shared-memory layout"): fragment row
+  // lane>>2 lives in shared-memory row frag_row(lane>>2) of its 8-row group, so that the 16 lanes of
+  // each half-warp (fragment rows 0-3 / 4-7) hit 16 distinct 8-byte bank pairs
   const uint32_t lane_const = (uint32_t) (q * ROW_BYTES + ((((l3 >> 1) ^ (q & 1)) << 4) | ((l3 & 1) << 3)));
   const uint32_t jx         = (uint32_t) (q >> 1);
 
@@ -271,8 +279,10 @@ __device__ __forceinline__ void consume_term(double (&acc)[32], const TaskParams
   for(int s = 0; s < td.kslabs; s++) {
     mbar_wait(full_bar + 8 * ring.stage, ring.phase, p.error_flag, 1);
     const uint32_t base = ring_base + ring.stage * (uint32_t) p.stage_bytes;
+    const uint32_t nj   = (s == td.kslabs - 1) ? (uint32_t) td.ksteps_last : 4u; // K tail: 4-wide steps only
 #pragma unroll
     for(uint32_t j = 0; j < 4; j++) {
+      if(j >= nj) break;
       const uint32_t jo = base + ((j ^ jx) << 5);
       double         fh[2][2], fg[2][2];
 #pragma unroll
@@ -406,7 +416,9 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
     const int g2 = grp % p.sub[2], g1 = (grp / p.sub[2]) % p.sub[1], g0 = grp / (p.sub[2] * p.sub[1]);
     sub_off[0] = 2 * g0, sub_off[1] = 2 * g1, sub_off[2] = 2 * g2;
   }
-  const int q6 = lane >> 2, l3 = lane & 3;
+  const int l3  = lane & 3;
+  const int q6  = frag_row(lane >> 2);            // particle offset of this lane's DMMA row
+  const int qc0 = frag_row(2 * l3);               // particle offset of DMMA column 2*l3 (+2 for column 2*l3+1)
 
   for(int box = blockIdx.x; box < p.nboxes; box += gridDim.x) {
     const BoxCoord bc = decode_box(p, box);
@@ -433,7 +445,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
 #pragma unroll
               for(int r = 0; r < 2; r++) {
                 const int hl = ((sub_off[0] + i1) * p.c[1] + sub_off[1] + i2) * p.c[2] + sub_off[2] + i3;
-                const int p4 = 2 * wq + ql, p5 = 2 * l3 + r;
+                const int p4 = 2 * wq + ql, p5 = qc0 + 2 * r;
                 scratch[((hl * 8 + p4) * 8 + p5) * 8 + q6] = acc[((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2) + r];
               }
       __syncthreads();
@@ -448,7 +460,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
 #pragma unroll
               for(int r = 0; r < 2; r++) {
                 const int hl = ((sub_off[0] + i1) * p.c[1] + sub_off[1] + i2) * p.c[2] + sub_off[2] + i3;
-                const int p5 = 2 * wq + ql, p4 = 2 * l3 + r;
+                const int p5 = 2 * wq + ql, p4 = qc0 + 2 * r;
                 acc[((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2) + r] = scratch[((hl * 8 + p4) * 8 + p5) * 8 + q6];
               }
       // generic-proxy accesses to the ring must be ordered before the TMA (async proxy) refills it
@@ -459,13 +471,69 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
     for(int t = p.nterms_x; t < p.nterms; t++)
       consume_dispatch(acc, p, p.term[t], ring, ring_base, full_bar, empty_bar, sub_off, wq, lane);
 
-    // ---------------- epilogue: s1, denominators, energy ----------------
+    // ---------------- epilogue: denominators, E[T], then the s1 part of E(T) ----------------
+    // E[T] += d*d/D ; E(T) += d*(d+s)/D = E[T] part + (d/D)*s.  Pass 1 turns every accumulator into
+    // t = d/D (0 for padding elements); pass 2 adds t * (a_k * b_k) term by term, walking the staged
+    // s1 operands with per-term strides (no per-element index arithmetic).
     const bool layout_y = p.nterms > p.nterms_x; // layout of the accumulators now
     const int  id_qt = layout_y ? 4 : 3, id_qc = layout_y ? 3 : 4;
-    double     e1 = 0.0, e2 = 0.0;
+    int        hc[3], tcq, ccq;                  // coordinates of element (0,0,0,0,0) of this thread
+    hc[0] = bc.off[0] + sub_off[0], hc[1] = bc.off[1] + sub_off[1], hc[2] = bc.off[2] + sub_off[2];
+    tcq = (layout_y ? bc.off[4] : bc.off[3]) + 2 * wq;
+    ccq = (layout_y ? bc.off[3] : bc.off[4]) + qc0;
     const int  c6 = bc.off[5] + q6;
-    if(c6 < p.ext[5]) {
-      const double ep6 = __ldg(p.evl[5] + c6);
+    double     eh[3][2], et[2], ec[2];
+    unsigned   vmask = 0; // bit layout: [h1:2][h2:2][h3:2][qt:2][qc:2]
+#pragma unroll
+    for(int j = 0; j < 3; j++)
+#pragma unroll
+      for(int i = 0; i < 2; i++) {
+        const bool ok = hc[j] + i < p.ext[j];
+        eh[j][i]      = ok ? __ldg(p.evl[j] + hc[j] + i) : 0.0;
+        vmask |= (unsigned) ok << (2 * j + i);
+      }
+#pragma unroll
+    for(int i = 0; i < 2; i++) {
+      const int     ext_t = layout_y ? p.ext[4] : p.ext[3], ext_c = layout_y ? p.ext[3] : p.ext[4];
+      const double* ev_t  = layout_y ? p.evl[4] : p.evl[3];
+      const double* ev_c  = layout_y ? p.evl[3] : p.evl[4];
+      const bool    okt = tcq + i < ext_t, okc = ccq + 2 * i < ext_c;
+      et[i]             = okt ? __ldg(ev_t + tcq + i) : 0.0;
+      ec[i]             = okc ? __ldg(ev_c + ccq + 2 * i) : 0.0;
+      vmask |= ((unsigned) okt << (6 + i)) | ((unsigned) okc << (8 + i));
+    }
+    const bool   ok6 = c6 < p.ext[5];
+    const double e6  = ok6 ? __ldg(p.evl[5] + c6) : 0.0;
+    double       e1 = 0.0, e2 = 0.0;
+#pragma unroll
+    for(int i1 = 0; i1 < 2; i1++)
+#pragma unroll
+      for(int i2 = 0; i2 < 2; i2++)
+#pragma unroll
+        for(int i3 = 0; i3 < 2; i3++)
+#pragma unroll
+          for(int ql = 0; ql < 2; ql++)
+#pragma unroll
+            for(int r = 0; r < 2; r++) {
+              const int      ai   = ((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2) + r;
+              const unsigned need = (1u << i1) | (1u << (2 + i2)) | (1u << (4 + i3)) | (1u << (6 + ql)) | (1u << (8 + r));
+              const bool     ok   = ok6 && (vmask & need) == need;
+              const double   d    = acc[ai];
+              const double   D    = eh[0][i1] + eh[1][i2] + eh[2][i3] - et[ql] - ec[r] - e6;
+              const double   tq   = ok ? d / D : 0.0;
+              e1 += tq * d;
+              acc[ai] = tq;
+            }
+    e2 = e1;
+    for(int k = 0; k < p.ns1; k++) {
+      const S1Dev&  sd = p.s1[k];
+      const double* pa = sd.a + (hc[0] * sd.sa[0] + hc[1] * sd.sa[1] + hc[2] * sd.sa[2] + tcq * sd.sa[id_qt] +
+                                 ccq * sd.sa[id_qc] + c6 * sd.sa[5]);
+      const double* pb = sd.b + (hc[0] * sd.sb[0] + hc[1] * sd.sb[1] + hc[2] * sd.sb[2] + tcq * sd.sb[id_qt] +
+                                 ccq * sd.sb[id_qc] + c6 * sd.sb[5]);
+      const int da[5] = {sd.sa[0], sd.sa[1], sd.sa[2], sd.sa[id_qt], 2 * sd.sa[id_qc]};
+      const int db[5] = {sd.sb[0], sd.sb[1], sd.sb[2], sd.sb[id_qt], 2 * sd.sb[id_qc]};
+      double    acc_s = 0.0;
 #pragma unroll
       for(int i1 = 0; i1 < 2; i1++)
 #pragma unroll
@@ -476,25 +544,12 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
             for(int ql = 0; ql < 2; ql++)
 #pragma unroll
               for(int r = 0; r < 2; r++) {
-                int coord[6];
-                coord[0]     = bc.off[0] + sub_off[0] + i1;
-                coord[1]     = bc.off[1] + sub_off[1] + i2;
-                coord[2]     = bc.off[2] + sub_off[2] + i3;
-                coord[id_qt] = bc.off[id_qt] + 2 * wq + ql;
-                coord[id_qc] = bc.off[id_qc] + 2 * l3 + r;
-                coord[5]     = c6;
-                if(coord[0] < p.ext[0] && coord[1] < p.ext[1] && coord[2] < p.ext[2] && coord[3] < p.ext[3] &&
-                   coord[4] < p.ext[4]) {
-                  const double d = acc[((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2) + r];
-                  const double s = s1_sum(p, coord);
-                  const double D = __ldg(p.evl[0] + coord[0]) + __ldg(p.evl[1] + coord[1]) +
-                                   __ldg(p.evl[2] + coord[2]) - __ldg(p.evl[3] + coord[3]) -
-                                   __ldg(p.evl[4] + coord[4]) - ep6;
-                  const double tmp = d / D;
-                  e1 += tmp * d;
-                  e2 += tmp * (d + s);
-                }
+                const int ai = ((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2) + r;
+                const int oa = i1 * da[0] + i2 * da[1] + i3 * da[2] + ql * da[3] + r * da[4];
+                const int ob = i1 * db[0] + i2 * db[1] + i3 * db[2] + ql * db[3] + r * db[4];
+                acc_s += acc[ai] * (__ldg(pa + oa) * __ldg(pb + ob));
               }
+      e2 += acc_s;
     }
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) {
@@ -631,6 +686,95 @@ cudaError_t probe_fp64_peak(int use_dmma, int iters, double* tflops, double* ms_
                                 : (double) grid * block * (double) iters * 16.0 * 2.0;
   *ms_out            = best;
   *tflops            = flops / (best * 1e-3) / 1e12;
+  return cudaGetLastError();
+}
+
+
+// Mainloop emulation: every warp repeats { TA + TB fragment loads from shared memory (swizzled,
+// conflict-free), TA*TB DMMAs } with no TMA, barriers or epilogue.  Shows how close a given
+// warps-per-SM / tiles-per-warp configuration can get to the DMMA peak.
+template<int TA, int TB>
+__global__ void __launch_bounds__(512) mainloop_probe_kernel(double* out, int iters) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  double*        sm   = reinterpret_cast<double*>(smem_raw + (base - smem_u32(smem_raw)));
+  for(int i = threadIdx.x; i < 64 * 16 * 4; i += blockDim.x) sm[i] = 1e-3 * (i % 7);
+  __syncthreads();
+  const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int      q = lane >> 2, l3 = lane & 3;
+  const int      pr = 2 * (q & 3) + (q >> 2);
+  const uint32_t lane_const = (uint32_t) (pr * ROW_BYTES + ((((l3 >> 1) ^ (pr & 1)) << 4) | ((l3 & 1) << 3)));
+  const uint32_t jx = (uint32_t) (pr >> 1);
+  double         acc[TA * TB * 2];
+#pragma unroll
+  for(int i = 0; i < TA * TB * 2; i++) acc[i] = 0.0;
+  uint32_t offa[TA], offb[TB];
+#pragma unroll
+  for(int i = 0; i < TA; i++) offa[i] = (uint32_t) (((warp * 3 + i) & 31) * 8 * ROW_BYTES) + lane_const;
+#pragma unroll
+  for(int i = 0; i < TB; i++) offb[i] = (uint32_t) (((warp * 5 + i + 32) & 63) * 8 * ROW_BYTES) + lane_const;
+  for(int it = 0; it < iters; it++) {
+#pragma unroll
+    for(uint32_t j = 0; j < 4; j++) {
+      const uint32_t jo = base + ((j ^ jx) << 5) + (uint32_t) ((it & 3) * 64 * ROW_BYTES);
+      double         fa[TA], fb[TB];
+#pragma unroll
+      for(int i = 0; i < TA; i++) fa[i] = lds_f64(jo + offa[i]);
+#pragma unroll
+      for(int i = 0; i < TB; i++) fb[i] = lds_f64(jo + offb[i]);
+#pragma unroll
+      for(int x = 0; x < TA; x++)
+#pragma unroll
+        for(int y = 0; y < TB; y++) dmma884(acc[2 * (x * TB + y)], acc[2 * (x * TB + y) + 1], fa[x], fb[y]);
+    }
+  }
+  double sacc = 0;
+#pragma unroll
+  for(int i = 0; i < TA * TB * 2; i++) sacc += acc[i];
+  out[(int64_t) blockIdx.x * blockDim.x + threadIdx.x] = sacc;
+}
+
+cudaError_t probe_mainloop(int ta, int tb, int warps_per_cta, int ctas_per_sm, int iters, double* tflops) {
+  cudaDeviceProp prop;
+  int            dev = 0;
+  cudaGetDevice(&dev);
+  cudaError_t err = cudaGetDeviceProperties(&prop, dev);
+  if(err != cudaSuccess) return err;
+  void (*k)(double*, int) = nullptr;
+  if(ta == 4 && tb == 4) k = mainloop_probe_kernel<4, 4>;
+  else if(ta == 2 && tb == 4) k = mainloop_probe_kernel<2, 4>;
+  else if(ta == 2 && tb == 2) k = mainloop_probe_kernel<2, 2>;
+  else if(ta == 4 && tb == 8) k = mainloop_probe_kernel<4, 8>;
+  else return cudaErrorInvalidValue;
+  // shared memory sized so that exactly ctas_per_sm CTAs fit
+  size_t smem = (size_t) prop.sharedMemPerMultiprocessor / ctas_per_sm - 2048;
+  if(smem > prop.sharedMemPerBlockOptin) smem = prop.sharedMemPerBlockOptin;
+  if(smem < 4 * 64 * ROW_BYTES + 1024) return cudaErrorInvalidValue;
+  if((err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return err;
+  const int grid = prop.multiProcessorCount * ctas_per_sm, block = 32 * warps_per_cta;
+  int       occ  = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, block, smem);
+  if(occ < ctas_per_sm) return cudaErrorLaunchOutOfResources;
+  double* out = nullptr;
+  if((err = cudaMalloc(&out, sizeof(double) * grid * block)) != cudaSuccess) return err;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for(int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    k<<<grid, block, smem>>>(out, iters);
+    cudaEventRecord(e1);
+    if((err = cudaEventSynchronize(e1)) != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if(rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if(err != cudaSuccess) return err;
+  *tflops = (double) grid * warps_per_cta * (double) iters * 4.0 * ta * tb * 512.0 / (best * 1e-3) / 1e12;
   return cudaGetLastError();
 }
 

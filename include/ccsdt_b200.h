@@ -129,6 +129,8 @@ CCSDT_API int ccsdt_run(ccsdt_ctx* ctx, int64_t task_begin, int64_t task_end, do
 
 /* diagnostics used by tests and bench (device microbenchmarks and unit probes) */
 CCSDT_API int ccsdt_probe_fp64_peak(int device, int use_dmma, int iters, double* tflops, double* ms);
+CCSDT_API int ccsdt_probe_mainloop(int device, int ta, int tb, int warps_per_cta, int ctas_per_sm, int iters,
+                                  double* tflops);
 CCSDT_API int ccsdt_probe_dmma_layout(int device, double* c_out /*64*/, const double* a /*8x4*/, const double* b /*4x8*/);
 CCSDT_API int ccsdt_probe_tma_swizzle(int device, double* smem_dump /*rows*16*/, int rows);
 CCSDT_API int ccsdt_synth_block(int device, uint64_t seed, int tensor, int noa, int nob, int nva, int nvb,
