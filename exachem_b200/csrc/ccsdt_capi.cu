@@ -604,15 +604,18 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
   }
   P.partial = b.d_partial;
 
-  if(ctx->opt.kernel == CCSDT_KERNEL_DMMA) {
-    const int ncw = 4 * P.sub[0] * P.sub[1] * P.sub[2];
-    int       rows = 0;
+  if(ctx->opt.kernel != CCSDT_KERNEL_SIMPLE) {
+    const bool ws  = ctx->opt.kernel == CCSDT_KERNEL_DMMA_WS; // dedicated producer warp (first generation)
+    const int  ncw = 4 * P.sub[0] * P.sub[1] * P.sub[2];
+    int        rows = 0;
     for(int hh = 0; hh < 3; hh++) {
       const int a = hh == 0 ? 1 : 0, c2 = hh == 2 ? 1 : 2;
       rows = std::max(rows, P.c[hh] * 64 + P.c[a] * P.c[c2] * 8);
     }
-    P.stage_bytes     = rows * ROW_BYTES;
-    int ctas          = ctx->opt.ctas_per_sm > 0 ? ctx->opt.ctas_per_sm : (ncw <= 4 ? 3 : 1);
+    P.stage_bytes = rows * ROW_BYTES;
+    int ctas      = ctx->opt.ctas_per_sm > 0 ? ctx->opt.ctas_per_sm
+                                             : (ws ? (ncw <= 4 ? 3 : 1) : (ncw == 4 ? 3 : ncw == 8 ? 2 : 1));
+    if(!ws) ctas = std::min(ctas, 16 / ncw); // 128 registers per thread: at most 16 warps per SM
     const size_t smem_total = (size_t) ctx->prop.sharedMemPerMultiprocessor;
     const size_t per_cta    = std::min((size_t) ctx->prop.sharedMemPerBlockOptin,
                                        smem_total / ctas - 1024 /*driver reserve*/) - 2048 /*static + slack*/;
@@ -622,10 +625,10 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     const int64_t box_elems = (int64_t) P.c[0] * P.c[1] * P.c[2] * 512;
     if(stages < 2 || (int64_t) stages * P.stage_bytes < box_elems * 8)
       return ctx->fail("shared memory too small for the requested CTA box", 8);
-    P.stages        = stages;
-    b.smem          = (size_t) stages * P.stage_bytes + 1024;
+    P.stages         = stages;
+    b.smem           = (size_t) stages * P.stage_bytes + 1024;
     b.consumer_warps = ncw;
-    b.grid          = (int) std::min<int64_t>(nboxes, (int64_t) ctx->prop.multiProcessorCount * ctas);
+    b.grid           = (int) std::min<int64_t>(nboxes, (int64_t) ctx->prop.multiProcessorCount * ctas);
   }
 
   // ---- launch the panel build on the staging stream ----
@@ -653,7 +656,10 @@ int launch_task(ccsdt_ctx* ctx, StageBuf& b, int64_t slot) {
   int nparts;
   if(ctx->opt.kernel == CCSDT_KERNEL_SIMPLE) { CK(launch_fused_simple(b.params, ctx->s_compute, &nparts)); }
   else {
-    CK(launch_fused_dmma(b.params, b.grid, b.consumer_warps, b.smem, ctx->s_compute));
+    if(ctx->opt.kernel == CCSDT_KERNEL_DMMA_WS) {
+      CK(launch_fused_dmma(b.params, b.grid, b.consumer_warps, b.smem, ctx->s_compute));
+    }
+    else { CK(launch_fused_dmma2(b.params, b.grid, b.consumer_warps, b.smem, ctx->s_compute)); }
     nparts = b.params.nboxes;
   }
   CK(cudaEventRecord(b.k1, ctx->s_compute));
@@ -730,7 +736,8 @@ int ccsdt_create(ccsdt_ctx** out, int device) {
   if((e = cudaStreamCreateWithFlags(&ctx->s_stage, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
   if((e = cudaMalloc(&ctx->d_error, 4)) != cudaSuccess) return bail(cudaGetErrorString(e));
   cudaMemset(ctx->d_error, 0, 4);
-  if((e = fused_dmma_configure((size_t) ctx->prop.sharedMemPerBlockOptin - 2048)) != cudaSuccess)
+  if((e = fused_dmma_configure((size_t) ctx->prop.sharedMemPerBlockOptin - 2048)) != cudaSuccess ||
+     (e = fused_dmma2_configure((size_t) ctx->prop.sharedMemPerBlockOptin - 2048)) != cudaSuccess)
     return bail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
@@ -768,7 +775,8 @@ int ccsdt_set_options(ccsdt_ctx* ctx, const ccsdt_options* o) {
     prod *= n.sub[i];
   }
   if(prod > 3) return ctx->fail("options.sub product must be <= 3 (at most 12 consumer warps)");
-  if(n.kernel != CCSDT_KERNEL_DMMA && n.kernel != CCSDT_KERNEL_SIMPLE) return ctx->fail("unknown kernel id");
+  if(n.kernel != CCSDT_KERNEL_DMMA && n.kernel != CCSDT_KERNEL_SIMPLE && n.kernel != CCSDT_KERNEL_DMMA_WS)
+    return ctx->fail("unknown kernel id");
   if(n.nranks < 1) n.nranks = 1;
   if(n.rank < 0 || n.rank >= n.nranks) return ctx->fail("rank out of range");
   if(n.stages < 0 || n.stages > MAX_STAGES) return ctx->fail("stages out of range");

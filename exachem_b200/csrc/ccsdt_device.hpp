@@ -104,6 +104,8 @@ cudaError_t launch_fused_dmma(const TaskParams& p, int grid, int consumer_warps,
 cudaError_t launch_fused_simple(const TaskParams& p, cudaStream_t st, int* grid_out);
 cudaError_t launch_reduce_partials(const double* partial, int n, double* out2, cudaStream_t st);
 cudaError_t fused_dmma_configure(size_t smem_bytes);
+cudaError_t fused_dmma2_configure(size_t smem_bytes);
+cudaError_t launch_fused_dmma2(const TaskParams& p, int grid, int warps, size_t smem_bytes, cudaStream_t st);
 int         fused_dmma_max_ctas_per_sm(int threads, size_t smem_bytes);
 
 cudaError_t probe_fp64_peak(int use_dmma, int iters, double* tflops, double* ms);

@@ -23,7 +23,7 @@ from . import _lib
 from ._lib import FETCH_FN, Options, Stats
 
 T1, T2, V_IJAB, V_IJKA, V_IABC = 0, 1, 2, 3, 4
-KERNEL_DMMA, KERNEL_SIMPLE = 0, 1
+KERNEL_DMMA, KERNEL_SIMPLE, KERNEL_DMMA_WS = 0, 1, 2
 
 
 class CcsdtError(RuntimeError):

@@ -62,7 +62,9 @@ enum {
   CCSDT_V_IABC = 4  /* v2iabc [O][V][V][V]    */
 };
 
-enum { CCSDT_KERNEL_DMMA = 0, CCSDT_KERNEL_SIMPLE = 1 };
+/* DMMA: the product kernel (all warps issue DMMA, warp 0 pumps the TMA ring); DMMA_WS: first-generation
+ * variant with a dedicated TMA producer warp; SIMPLE: diagnostic one-thread-per-element FMA kernel */
+enum { CCSDT_KERNEL_DMMA = 0, CCSDT_KERNEL_SIMPLE = 1, CCSDT_KERNEL_DMMA_WS = 2 };
 
 typedef struct ccsdt_options {
   int32_t kernel;        /* CCSDT_KERNEL_DMMA (product) or CCSDT_KERNEL_SIMPLE (diagnostic FMA kernel) */

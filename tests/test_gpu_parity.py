@@ -95,13 +95,14 @@ BOXES = [(1, 1, 1), (1, 1, 2), (2, 1, 1), (1, 1, 3), (1, 3, 1)]
 
 
 @pytest.mark.parametrize("name", sorted(GOLD))
-@pytest.mark.parametrize("kernel", ["simple", "dmma"])
+@pytest.mark.parametrize("kernel", ["simple", "dmma", "dmma_ws"])
 def test_energy_matches_reference_fixture(name, kernel):
     g = GOLD[name]
     sp = drv.setup_mo_space(g["noa"], g["nob"], g["nva"], g["nvb"], g["tilesize"])
     T = syn.dense_all(syn.Orbitals(g["noa"], g["nob"], g["nva"], g["nvb"]), g["seed"])
     e1, e2, stats, pt = run_gpu(sp, T, g["restricted"],
-                                kernel=drv.KERNEL_SIMPLE if kernel == "simple" else drv.KERNEL_DMMA)
+                                kernel={"simple": drv.KERNEL_SIMPLE, "dmma": drv.KERNEL_DMMA,
+                                        "dmma_ws": drv.KERNEL_DMMA_WS}[kernel])
     assert _close(e1, float(g["energy1"])) and _close(e2, float(g["energy2"]))
     run1 = np.cumsum(pt[:, 0])
     assert np.allclose(run1, [float(x) for x in g["running_e1"]], rtol=0, atol=ATOL)   # task by task
@@ -109,17 +110,30 @@ def test_energy_matches_reference_fixture(name, kernel):
     assert stats["counted_flops"] == g["total_num_ops"]
 
 
+@pytest.mark.parametrize("kernel", [drv.KERNEL_DMMA, drv.KERNEL_DMMA_WS])
 @pytest.mark.parametrize("sub", BOXES)
 @pytest.mark.parametrize("cfg", [(4, 4, 6, 6, 3, True, 11), (5, 5, 11, 11, 8, True, 99), (3, 3, 5, 5, 2, False, 8),
                                  (6, 6, 17, 17, 9, True, 21), (9, 9, 10, 10, 10, True, 5)])
-def test_dmma_kernel_all_box_shapes(orc, cfg, sub):
+def test_dmma_kernel_all_box_shapes(orc, cfg, sub, kernel):
     oa, ob, va, vb, ts, restricted, seed = cfg
     sp, osp = drv.setup_mo_space(oa, ob, va, vb, ts), orc.tiles(oa, ob, va, vb, ts)
     T = syn.dense_all(syn.Orbitals(oa, ob, va, vb), seed)
     ref = orc.run(osp, T, restricted, per_task=True)
-    e1, e2, _, pt = run_gpu(sp, T, restricted, sub=sub)
+    e1, e2, _, pt = run_gpu(sp, T, restricted, sub=sub, kernel=kernel)
     assert _close(e1, ref[0]) and _close(e2, ref[1])
     assert np.allclose(pt, ref[2], rtol=0, atol=ATOL)
+
+
+@pytest.mark.parametrize("opts", [dict(stages=2), dict(sub=(1, 1, 1), ctas_per_sm=4), dict(sub=(1, 1, 2), ctas_per_sm=1),
+                                  dict(sub=(1, 1, 1), ctas_per_sm=1, stages=2)])
+def test_ring_depth_and_occupancy_variants(orc, opts):
+    """the TMA ring must be correct at its minimum depth and at every CTA-per-SM setting"""
+    oa, ob, va, vb, ts = 6, 6, 17, 17, 9
+    sp, osp = drv.setup_mo_space(oa, ob, va, vb, ts), orc.tiles(oa, ob, va, vb, ts)
+    T = syn.dense_all(syn.Orbitals(oa, ob, va, vb), 21)
+    ref = orc.run(osp, T, True)
+    e1, e2, _, _ = run_gpu(sp, T, True, **opts)
+    assert _close(e1, ref[0]) and _close(e2, ref[1])
 
 
 def test_ragged_tiles_and_single_orbital_tiles(orc):
