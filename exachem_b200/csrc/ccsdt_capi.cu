@@ -711,7 +711,8 @@ int ccsdt_create(ccsdt_ctx** out, int device) {
                      "); this library has no CPU fallback";
     return 2;
   }
-  if(device < 0 || device >= ndev) {
+  if(device < 0 && cudaGetDevice(&device) != cudaSuccess) device = 0; // negative: the caller's current device
+  if(device >= ndev) {
     g_create_error = "device index out of range";
     return 2;
   }

@@ -1,0 +1,176 @@
+// ccsd_t_fused_driver_b200.hpp -- drop-in replacement for ExaChem's
+//   exachem/cc/ccsd_t/ccsd_t_fused_driver.hpp
+// Same class name, same two member signatures (reference lines 73-81 and 83-87), same return tuple
+// (energy1 = E[T] rank-partial, energy2 = E(T) rank-partial, work seconds, total seconds; reference
+// line 545), so exachem/cc/ccsd_t/ccsd_t.cpp:253-256 and :298-301 compile and behave unchanged.  The
+// body is a thin adapter: it reads the tile space from TAMM, serves tensor blocks to the library
+// through Tensor<T>::get, and calls the C ABI of include/ccsdt_b200.h.  All arithmetic happens in
+// libccsdt_b200.so on the GPU; there is no CPU path here.
+//
+// Contract kept from the reference:
+//   * one host rank drives one GPU (the rank's current CUDA device, as TAMM bound it);
+//   * the returned energies are rank PARTIALS -- the caller sums them over ranks
+//     (ccsd_t.cpp:262-263); the library's static cost-balanced split replaces the GA atomic counter
+//     (reference lines 169-172, 381, 456);
+//   * the six LRUCache arguments are accepted and ignored: the library's HBM block store caches
+//     every fetched block for the whole call (the reference caches sorted copies on the host);
+//   * hf_ccsd_energy, seq_h3b and tilesize_opt are unused, as in the reference body;
+//   * errors are fatal: a non-zero C-ABI status becomes tamm_terminate(message), matching
+//     CUDA_SAFE -> exit(100) (ccsd_t_common.hpp:26-31) and ccsd_t.cpp:27-28.
+//
+// Requirements on the including translation unit (the same the reference header has): the TAMM
+// umbrella header (Index, IndexVector, Tensor, LRUCache, TiledIndexSpace, ExecutionContext),
+// ChemEnv and exachem::cholesky_2e::V2Tensors must be declared before this header is included.
+#pragma once
+
+#include "ccsdt_b200.h"
+
+#include <cstring>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#ifndef CCSDT_B200_TERMINATE
+// real TAMM provides tamm::tamm_terminate(std::string); a test shim may define this macro instead
+#define CCSDT_B200_TERMINATE(msg) tamm_terminate(msg)
+#endif
+
+namespace ccsdt_b200_detail {
+
+template<typename T>
+struct FetchUser {
+  Tensor<T>*     tensor[5];
+  std::vector<T> buf;
+};
+
+// ccsdt_fetch_fn trampoline: one unsorted row-major block, exactly what Tensor<T>::get returns
+// (the reference's call sites: ccsd_t_all_fused_singles.hpp:200,304; ..._doubles1.hpp:222,237,282;
+//  ..._doubles2.hpp:215,230,335)
+template<typename T>
+int fetch_block(void* user, int tensor, const uint32_t bid[4], double* dst, size_t n) {
+  auto*       u  = static_cast<FetchUser<T>*>(user);
+  const int   nd = tensor == CCSDT_T1 ? 2 : 4;
+  IndexVector id(nd);
+  for(int i = 0; i < nd; i++) id[i] = (Index) bid[i];
+  if(u->buf.size() < n) u->buf.resize(n);
+  u->tensor[tensor]->get(id, u->buf);
+  for(size_t i = 0; i < n; i++) dst[i] = (double) u->buf[i];
+  return 0;
+}
+
+struct TileSpace {
+  int                  noa, nob, nva, nvb;
+  std::vector<int64_t> k_range;
+  std::vector<int32_t> k_spin;
+};
+
+inline TileSpace read_space(const TiledIndexSpace& MO, const std::vector<int>& k_spin) {
+  TileSpace  s;
+  const int  noab = (int) MO("occ").num_tiles(), nvab = (int) MO("virt").num_tiles();
+  s.noa = (int) MO("occ_alpha").num_tiles();
+  s.nva = (int) MO("virt_alpha").num_tiles();
+  s.nob = noab - s.noa;
+  s.nvb = nvab - s.nva;
+  for(auto x: MO.input_tile_sizes()) s.k_range.push_back((int64_t) x);
+  for(auto x: k_spin) s.k_spin.push_back((int32_t) x);
+  return s;
+}
+
+} // namespace ccsdt_b200_detail
+
+template<typename T>
+class CCSD_T_Fused_Driver {
+public:
+  CCSD_T_Fused_Driver() = default;
+
+  virtual ~CCSD_T_Fused_Driver() = default;
+
+  CCSD_T_Fused_Driver(const CCSD_T_Fused_Driver&)            = default;
+  CCSD_T_Fused_Driver& operator=(const CCSD_T_Fused_Driver&) = default;
+  CCSD_T_Fused_Driver(CCSD_T_Fused_Driver&&)                 = default;
+  CCSD_T_Fused_Driver& operator=(CCSD_T_Fused_Driver&&)      = default;
+
+  virtual std::tuple<T, T, double, double>
+  execute(ChemEnv& chem_env, ExecutionContext& ec, std::vector<int>& k_spin,
+          const TiledIndexSpace& MO, Tensor<T>& d_t1, Tensor<T>& d_t2,
+          exachem::cholesky_2e::V2Tensors<T>& d_v2, std::vector<T>& k_evl_sorted, T hf_ccsd_energy,
+          bool is_restricted, LRUCache<Index, std::vector<T>>& cache_s1t,
+          LRUCache<Index, std::vector<T>>& cache_s1v, LRUCache<Index, std::vector<T>>& cache_d1t,
+          LRUCache<Index, std::vector<T>>& cache_d1v, LRUCache<Index, std::vector<T>>& cache_d2t,
+          LRUCache<Index, std::vector<T>>& cache_d2v, bool seq_h3b = false,
+          bool tilesize_opt = true);
+
+  virtual void calculate_performance_ops(ChemEnv& chem_env, ExecutionContext& ec,
+                                         std::vector<int>& k_spin, const TiledIndexSpace& MO,
+                                         std::vector<T>& k_evl_sorted, double hf_ccsd_energy,
+                                         bool is_restricted, long double& total_num_ops,
+                                         bool seq_h3b = false);
+
+  // statistics of the last execute() on this object (not part of the reference interface)
+  ccsdt_stats last_stats{};
+};
+
+template<typename T>
+std::tuple<T, T, double, double> CCSD_T_Fused_Driver<T>::execute(
+  ChemEnv& chem_env, ExecutionContext& ec, std::vector<int>& k_spin, const TiledIndexSpace& MO,
+  Tensor<T>& d_t1, Tensor<T>& d_t2, exachem::cholesky_2e::V2Tensors<T>& d_v2,
+  std::vector<T>& k_evl_sorted, T hf_ccsd_energy, bool is_restricted,
+  LRUCache<Index, std::vector<T>>& cache_s1t, LRUCache<Index, std::vector<T>>& cache_s1v,
+  LRUCache<Index, std::vector<T>>& cache_d1t, LRUCache<Index, std::vector<T>>& cache_d1v,
+  LRUCache<Index, std::vector<T>>& cache_d2t, LRUCache<Index, std::vector<T>>& cache_d2v,
+  bool seq_h3b, bool tilesize_opt) {
+  (void) chem_env; (void) hf_ccsd_energy; (void) seq_h3b; (void) tilesize_opt;
+  (void) cache_s1t; (void) cache_s1v; (void) cache_d1t; (void) cache_d1v; (void) cache_d2t; (void) cache_d2v;
+  using namespace ccsdt_b200_detail;
+
+  const TileSpace     s = read_space(MO, k_spin);
+  std::vector<double> evl(k_evl_sorted.begin(), k_evl_sorted.end());
+
+  ccsdt_ctx* ctx = nullptr;
+  if(ccsdt_create(&ctx, /*device=*/-1 /* the rank's current CUDA device */))
+    CCSDT_B200_TERMINATE(std::string("[CCSD(T) B200] ") + ccsdt_last_error(nullptr));
+  auto check = [&](int rc) {
+    if(rc) {
+      std::string msg = std::string("[CCSD(T) B200] ") + ccsdt_last_error(ctx);
+      ccsdt_destroy(ctx);
+      CCSDT_B200_TERMINATE(msg);
+    }
+  };
+
+  ccsdt_options opt;
+  ccsdt_default_options(&opt);
+  opt.rank   = (int32_t) ec.pg().rank().value();
+  opt.nranks = (int32_t) ec.pg().size().value();
+  check(ccsdt_set_options(ctx, &opt));
+  check(ccsdt_set_space(ctx, s.noa, s.nob, s.nva, s.nvb, s.k_range.data(), s.k_spin.data(), evl.data(),
+                        is_restricted ? 1 : 0));
+
+  FetchUser<T> user;
+  user.tensor[CCSDT_T1]     = &d_t1;
+  user.tensor[CCSDT_T2]     = &d_t2;
+  user.tensor[CCSDT_V_IJAB] = &d_v2.v2ijab;
+  user.tensor[CCSDT_V_IJKA] = &d_v2.v2ijka;
+  user.tensor[CCSDT_V_IABC] = &d_v2.v2iabc;
+  check(ccsdt_set_fetch(ctx, &fetch_block<T>, &user));
+
+  double energies[2] = {0.0, 0.0};
+  check(ccsdt_run(ctx, 0, -1, energies, nullptr, &last_stats));
+  ccsdt_destroy(ctx);
+  ec.pg().barrier(); // the reference ends its timed region with a barrier (line 536)
+
+  return std::make_tuple((T) energies[0], (T) energies[1], last_stats.seconds_kernel + last_stats.seconds_staging,
+                         last_stats.seconds_total);
+}
+
+template<typename T>
+void CCSD_T_Fused_Driver<T>::calculate_performance_ops(ChemEnv& chem_env, ExecutionContext& ec,
+                                                       std::vector<int>& k_spin, const TiledIndexSpace& MO,
+                                                       std::vector<T>& k_evl_sorted, double hf_ccsd_energy,
+                                                       bool is_restricted, long double& total_num_ops,
+                                                       bool seq_h3b) {
+  (void) chem_env; (void) ec; (void) k_evl_sorted; (void) hf_ccsd_energy; (void) seq_h3b;
+  const auto s = ccsdt_b200_detail::read_space(MO, k_spin);
+  if(ccsdt_count_ops(s.noa + s.nob, s.nva + s.nvb, s.k_spin.data(), s.k_range.data(), is_restricted ? 1 : 0,
+                     &total_num_ops))
+    CCSDT_B200_TERMINATE(std::string("[CCSD(T) B200] ccsdt_count_ops failed"));
+}

@@ -91,7 +91,7 @@ typedef struct ccsdt_stats {
 /* delivers one UNSORTED row-major block, i.e. what Tensor<T>::get(bid, buf) returns */
 typedef int (*ccsdt_fetch_fn)(void* user, int tensor, const uint32_t bid[4], double* dst, size_t n);
 
-CCSDT_API int         ccsdt_create(ccsdt_ctx** out, int device);
+CCSDT_API int         ccsdt_create(ccsdt_ctx** out, int device); /* device < 0: the calling thread's current CUDA device */
 CCSDT_API int         ccsdt_destroy(ccsdt_ctx* ctx);
 CCSDT_API const char* ccsdt_last_error(const ccsdt_ctx* ctx); /* ctx may be NULL: error of the last failed create */
 CCSDT_API int         ccsdt_default_options(ccsdt_options* opt);

@@ -1,0 +1,131 @@
+// Test harness for include/ccsd_t_fused_driver_b200.hpp: compiles the drop-in header against the
+// TAMM stand-in the oracle uses (oracle/shim/tamm/tamm.hpp -- test infrastructure) and exposes the
+// same extern "C" entry the reference harness has (oracle/ref_driver.cpp: ref_ccsdt_execute), so a
+// parity test can call "reference execute" and "B200 execute" with identical arguments.
+// Links against exachem_b200/libccsdt_b200.so; nothing here computes.
+#include "tamm/tamm.hpp"
+
+#include <stdexcept>
+
+#define CCSDT_B200_TERMINATE(msg) throw std::runtime_error(msg)
+#include "ccsd_t_fused_driver_b200.hpp"
+
+namespace {
+
+struct Space {
+  int                 noab = 0, nvab = 0;
+  std::vector<size_t> k_range, k_offset;
+  std::vector<int>    k_spin;
+  size_t              Ot = 0, Vt = 0;
+};
+
+Space make_space(int noab, int nvab, const int64_t* k_range, const int32_t* k_spin) {
+  Space s;
+  s.noab = noab, s.nvab = nvab;
+  size_t sum = 0;
+  for(int i = 0; i < noab + nvab; i++) {
+    s.k_range.push_back((size_t) k_range[i]);
+    s.k_offset.push_back(sum);
+    sum += (size_t) k_range[i];
+    s.k_spin.push_back(k_spin[i]);
+    (i < noab ? s.Ot : s.Vt) += (size_t) k_range[i];
+  }
+  return s;
+}
+
+// a TAMM-like tensor over a dense row-major spin-orbital array; kinds[d] in {'o','v'}
+Tensor<double> dense_tensor(const Space& s, const double* data, std::string kinds) {
+  return Tensor<double>([&s, data, kinds](const IndexVector& bid, std::vector<double>& buf) {
+    const int d = (int) kinds.size();
+    size_t    ext[4], off[4], stride[4], st = 1, n = 1;
+    for(int i = d - 1; i >= 0; i--) {
+      const bool   occ  = kinds[i] == 'o';
+      const size_t tile = occ ? bid[i] : bid[i] + s.noab;
+      ext[i]    = s.k_range[tile];
+      off[i]    = s.k_offset[tile] - (occ ? 0 : s.Ot);
+      stride[i] = st;
+      st *= occ ? s.Ot : s.Vt;
+      n *= ext[i];
+    }
+    if(buf.size() < n) buf.resize(n);
+    std::vector<size_t> idx(d, 0);
+    for(size_t lin = 0; lin < n; lin++) {
+      size_t o = 0;
+      for(int i = 0; i < d; i++) o += (off[i] + idx[i]) * stride[i];
+      buf[lin] = data[o];
+      for(int i = d - 1; i >= 0 && ++idx[i] == ext[i]; i--) idx[i] = 0;
+    }
+  });
+}
+
+std::string g_error;
+
+} // namespace
+
+extern "C" {
+
+__attribute__((visibility("default"))) const char* adapter_last_error() { return g_error.c_str(); }
+
+// out[0..3] = the tuple execute returns; gets[0..4] = Tensor::get calls per tensor; stats_out (optional)
+__attribute__((visibility("default"))) int
+adapter_ccsdt_execute(int noa, int nob, int nva, int nvb, const int64_t* k_range, const int32_t* k_spin,
+                      const double* evl, const double* t1, const double* t2, const double* v2ijab,
+                      const double* v2ijka, const double* v2iabc, int is_restricted, int tilesize, double* out,
+                      int64_t* gets, long double* total_num_ops, ccsdt_stats* stats_out) {
+  try {
+    Space             s = make_space(noa + nob, nva + nvb, k_range, k_spin);
+    std::vector<Tile> tiles(s.k_range.begin(), s.k_range.end());
+    TiledIndexSpace   MO(tiles, noa, nob, nva, nvb);
+    ExecutionContext  ec;
+    ChemEnv           chem_env;
+    chem_env.ioptions.ccsd_options.ccsdt_tilesize = tilesize;
+    Tensor<double>                          d_t1 = dense_tensor(s, t1, "vo");
+    Tensor<double>                          d_t2 = dense_tensor(s, t2, "vvoo");
+    exachem::cholesky_2e::V2Tensors<double> d_v2;
+    d_v2.v2ijab = dense_tensor(s, v2ijab, "oovv");
+    d_v2.v2ijka = dense_tensor(s, v2ijka, "ooov");
+    d_v2.v2iabc = dense_tensor(s, v2iabc, "ovvv");
+    std::vector<double> k_evl(evl, evl + s.Ot + s.Vt);
+    // the caller's caches (exachem/cc/ccsd_t/ccsd_t.cpp:236-241); the adapter ignores them
+    LRUCache<Index, std::vector<double>> c1{8}, c2{8}, c3{8}, c4{8}, c5{8}, c6{8};
+
+    CCSD_T_Fused_Driver<double> drv;
+    // same call as exachem/cc/ccsd_t/ccsd_t.cpp:253-256
+    auto [e1, e2, tw, tt] = drv.execute(chem_env, ec, s.k_spin, MO, d_t1, d_t2, d_v2, k_evl, 0.0,
+                                        is_restricted != 0, c1, c2, c3, c4, c5, c6, true);
+    out[0] = e1, out[1] = e2, out[2] = tw, out[3] = tt;
+    if(gets) {
+      gets[0] = (int64_t) d_t1.num_gets, gets[1] = (int64_t) d_t2.num_gets;
+      gets[2] = (int64_t) d_v2.v2ijab.num_gets, gets[3] = (int64_t) d_v2.v2ijka.num_gets;
+      gets[4] = (int64_t) d_v2.v2iabc.num_gets;
+    }
+    if(stats_out) *stats_out = drv.last_stats;
+    if(total_num_ops) // same call as ccsd_t.cpp:298-301
+      drv.calculate_performance_ops(chem_env, ec, s.k_spin, MO, k_evl, 0.0, is_restricted != 0, *total_num_ops, true);
+    return 0;
+  } catch(const std::exception& e) {
+    g_error = e.what();
+    return 1;
+  }
+}
+
+// host-only: just the op counter through the adapter (usable without a GPU)
+__attribute__((visibility("default"))) int
+adapter_ccsdt_count_ops(int noa, int nob, int nva, int nvb, const int64_t* k_range, const int32_t* k_spin,
+                        int is_restricted, long double* total_num_ops) {
+  try {
+    Space               s = make_space(noa + nob, nva + nvb, k_range, k_spin);
+    std::vector<Tile>   tiles(s.k_range.begin(), s.k_range.end());
+    TiledIndexSpace     MO(tiles, noa, nob, nva, nvb);
+    ExecutionContext    ec;
+    ChemEnv             chem_env;
+    std::vector<double> k_evl(s.Ot + s.Vt, 0.0);
+    CCSD_T_Fused_Driver<double> drv;
+    drv.calculate_performance_ops(chem_env, ec, s.k_spin, MO, k_evl, 0.0, is_restricted != 0, *total_num_ops, true);
+    return 0;
+  } catch(const std::exception& e) {
+    g_error = e.what();
+    return 1;
+  }
+}
+}
