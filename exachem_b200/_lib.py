@@ -47,6 +47,7 @@ SIGNATURES = {
     "ccsdt_put_block": (C.c_int, [C.c_void_p, C.c_int, _u32p, _dp]),
     "ccsdt_set_fetch": (C.c_int, [C.c_void_p, FETCH_FN, C.c_void_p]),
     "ccsdt_set_synthetic": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "ccsdt_set_task_counter": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ccsdt_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _dp, C.POINTER(Stats)]),
     "ccsdt_probe_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp]),
     "ccsdt_probe_mainloop": (C.c_int, [C.c_int] * 6 + [_dp]),

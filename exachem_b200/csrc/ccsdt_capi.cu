@@ -53,6 +53,8 @@ struct StageBuf {
   int          desc_cap = 0;
   double*      d_partial = nullptr;
   int64_t      partial_cap = 0;
+  uint32_t*    d_counter = nullptr; // dynamic box scheduler of the fused kernel
+  int64_t      nparts = 0;          // entries of d_partial the reduction reads
   CUtensorMap  tmap[4];
   cudaEvent_t  staged = nullptr, done = nullptr, k0 = nullptr, k1 = nullptr, g0 = nullptr, g1 = nullptr;
   bool         timing_pending = false;
@@ -93,6 +95,7 @@ struct ccsdt_ctx {
   uint32_t*    d_error = nullptr;
   cudaStream_t s_compute = nullptr, s_stage = nullptr;
   void*        encode_fn = nullptr;
+  int64_t*     task_counter = nullptr; // process-shared dynamic task counter (NULL = static split)
   ccsdt_stats  stats{};
 
   int fail(const std::string& m, int code = 1) {
@@ -128,6 +131,8 @@ void free_pools(ccsdt_ctx* ctx) {
     if(b.d_descs) cudaFree(b.d_descs);
     if(b.h_descs) cudaFreeHost(b.h_descs);
     if(b.d_partial) cudaFree(b.d_partial);
+    if(b.d_counter) cudaFree(b.d_counter);
+    b.d_counter = nullptr;
     b.s1_a = b.s1_b = nullptr;
     b.d_descs = b.h_descs = nullptr;
     b.d_partial           = nullptr;
@@ -225,6 +230,7 @@ int ensure_pools(ccsdt_ctx* ctx) {
     b.desc_cap = 64 + 9 * 2 * 2 * (sp.noab() + sp.nvab() + 2);
     CK(cudaMalloc(&b.d_descs, sizeof(GatherDesc) * b.desc_cap));
     CK(cudaMallocHost(&b.h_descs, sizeof(GatherDesc) * b.desc_cap));
+    CK(cudaMalloc(&b.d_counter, 4));
     if(int rc = make_tmaps(ctx, b)) return rc;
     if(!b.staged) {
       CK(cudaEventCreateWithFlags(&b.staged, cudaEventDisableTiming));
@@ -588,34 +594,24 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     if(int rc = add_gather(ctx, b, nd, max_elems, pb, ds_b, v)) return rc;
   }
 
-  // ---- partial buffer + launch geometry ----
+  // ---- launch geometry, box order, partial buffer ----
   int64_t need_partial;
   if(ctx->opt.kernel == CCSDT_KERNEL_SIMPLE) {
     int64_t total = 1;
     for(int i = 0; i < 6; i++) total *= ext[i];
     need_partial = (total + 255) / 256;
   }
-  else need_partial = nboxes;
-  if(need_partial > b.partial_cap) {
-    CK(cudaStreamSynchronize(ctx->s_compute));
-    if(b.d_partial) CK(cudaFree(b.d_partial));
-    b.partial_cap = need_partial + need_partial / 4 + 64;
-    CK(cudaMalloc(&b.d_partial, (size_t) b.partial_cap * 16));
-  }
-  P.partial = b.d_partial;
-
-  if(ctx->opt.kernel != CCSDT_KERNEL_SIMPLE) {
-    const bool ws  = ctx->opt.kernel == CCSDT_KERNEL_DMMA_WS; // dedicated producer warp (first generation)
-    const int  ncw = 4 * P.sub[0] * P.sub[1] * P.sub[2];
-    int        rows = 0;
+  else {
+    const int ncw  = 4 * P.sub[0] * P.sub[1] * P.sub[2];
+    int       rows = 0;
     for(int hh = 0; hh < 3; hh++) {
       const int a = hh == 0 ? 1 : 0, c2 = hh == 2 ? 1 : 2;
       rows = std::max(rows, P.c[hh] * 64 + P.c[a] * P.c[c2] * 8);
     }
     P.stage_bytes = rows * ROW_BYTES;
-    int ctas      = ctx->opt.ctas_per_sm > 0 ? ctx->opt.ctas_per_sm
-                                             : (ws ? (ncw <= 4 ? 3 : 1) : (ncw == 4 ? 3 : ncw == 8 ? 2 : 1));
-    if(!ws) ctas = std::min(ctas, 16 / ncw); // 128 registers per thread: at most 16 warps per SM
+    // 128 registers per thread: 3 CTAs of 4+1 warps or 1 CTA of 8+1 / 12+1 warps per SM
+    int ctas = ctx->opt.ctas_per_sm > 0 ? ctx->opt.ctas_per_sm : (ncw <= 4 ? 3 : 1);
+    ctas     = std::min(ctas, ncw <= 4 ? 3 : 1);
     const size_t smem_total = (size_t) ctx->prop.sharedMemPerMultiprocessor;
     const size_t per_cta    = std::min((size_t) ctx->prop.sharedMemPerBlockOptin,
                                        smem_total / ctas - 1024 /*driver reserve*/) - 2048 /*static + slack*/;
@@ -628,8 +624,40 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     P.stages         = stages;
     b.smem           = (size_t) stages * P.stage_bytes + 1024;
     b.consumer_warps = ncw;
-    b.grid           = (int) std::min<int64_t>(nboxes, (int64_t) ctx->prop.multiProcessorCount * ctas);
+    const int64_t in_flight = (int64_t) ctx->prop.multiProcessorCount * ctas;
+    b.grid           = (int) std::min<int64_t>(nboxes, in_flight);
+    // bricks: grow the index with the smallest element extent until one brick holds about as many
+    // boxes as there are CTAs in flight, then even the bricks out over each index
+    const int cext[6] = {P.c[0], P.c[1], P.c[2], PBOX, PBOX, PBOX};
+    int64_t   vol     = 1;
+    for(int i = 0; i < 6; i++) P.brick[i] = 1;
+    while(vol < in_flight) {
+      int best = -1;
+      for(int i = 0; i < 6; i++)
+        if(P.brick[i] < P.nbox[i] && (best < 0 || cext[i] * P.brick[i] < cext[best] * P.brick[best])) best = i;
+      if(best < 0) break;
+      vol = vol / P.brick[best] * (P.brick[best] + 1);
+      P.brick[best]++;
+    }
+    int64_t padded = 1;
+    for(int i = 0; i < 6; i++) {
+      P.nbrick[i] = (P.nbox[i] + P.brick[i] - 1) / P.brick[i];
+      P.brick[i]  = (P.nbox[i] + P.nbrick[i] - 1) / P.nbrick[i];
+      padded *= (int64_t) P.nbrick[i] * P.brick[i];
+    }
+    if(padded > 0x7fffffff) return ctx->fail("task has too many CTA boxes", 7);
+    P.nboxes_padded = (int) padded;
+    P.box_counter   = b.d_counter;
+    need_partial    = padded;
   }
+  b.nparts = need_partial;
+  if(need_partial > b.partial_cap) {
+    CK(cudaStreamSynchronize(ctx->s_compute));
+    if(b.d_partial) CK(cudaFree(b.d_partial));
+    b.partial_cap = need_partial + need_partial / 4 + 64;
+    CK(cudaMalloc(&b.d_partial, (size_t) b.partial_cap * 16));
+  }
+  P.partial = b.d_partial;
 
   // ---- launch the panel build on the staging stream ----
   CK(cudaMemcpyAsync(b.d_descs, b.h_descs, sizeof(GatherDesc) * nd, cudaMemcpyHostToDevice, ctx->s_stage));
@@ -652,18 +680,27 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
 
 int launch_task(ccsdt_ctx* ctx, StageBuf& b, int64_t slot) {
   CK(cudaStreamWaitEvent(ctx->s_compute, b.staged, 0));
-  CK(cudaEventRecord(b.k0, ctx->s_compute));
-  int nparts;
-  if(ctx->opt.kernel == CCSDT_KERNEL_SIMPLE) { CK(launch_fused_simple(b.params, ctx->s_compute, &nparts)); }
-  else {
-    if(ctx->opt.kernel == CCSDT_KERNEL_DMMA_WS) {
-      CK(launch_fused_dmma(b.params, b.grid, b.consumer_warps, b.smem, ctx->s_compute));
-    }
-    else { CK(launch_fused_dmma2(b.params, b.grid, b.consumer_warps, b.smem, ctx->s_compute)); }
-    nparts = b.params.nboxes;
+  if(ctx->opt.kernel == CCSDT_KERNEL_SIMPLE) {
+    int nparts = 0;
+    CK(cudaEventRecord(b.k0, ctx->s_compute));
+    CK(launch_fused_simple(b.params, ctx->s_compute, &nparts));
+    CK(cudaEventRecord(b.k1, ctx->s_compute));
   }
-  CK(cudaEventRecord(b.k1, ctx->s_compute));
-  CK(launch_reduce_partials(b.d_partial, nparts, ctx->d_task_energy + 2 * slot, ctx->s_compute));
+  else if(b.params.nterms == 0) {
+    // no doubles contraction is enabled: d = 0 for every element, so E[T] and E(T) of the task are exactly 0
+    CK(cudaEventRecord(b.k0, ctx->s_compute));
+    CK(cudaMemsetAsync(b.d_partial, 0, (size_t) b.nparts * 16, ctx->s_compute));
+    CK(cudaEventRecord(b.k1, ctx->s_compute));
+  }
+  else {
+    // ids of the padded brick grid that are not boxes are never written: their partials stay zero
+    CK(cudaMemsetAsync(b.d_partial, 0, (size_t) b.nparts * 16, ctx->s_compute));
+    CK(cudaMemsetAsync(b.d_counter, 0, 4, ctx->s_compute));
+    CK(cudaEventRecord(b.k0, ctx->s_compute));
+    CK(launch_fused_dmma(b.params, b.grid, b.consumer_warps, b.smem, ctx->s_compute));
+    CK(cudaEventRecord(b.k1, ctx->s_compute));
+  }
+  CK(launch_reduce_partials(b.d_partial, (int) b.nparts, ctx->d_task_energy + 2 * slot, ctx->s_compute));
   CK(cudaEventRecord(b.done, ctx->s_compute));
   b.timing_pending = true;
   ctx->stats.kernel_launches += 2;
@@ -737,8 +774,7 @@ int ccsdt_create(ccsdt_ctx** out, int device) {
   if((e = cudaStreamCreateWithFlags(&ctx->s_stage, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
   if((e = cudaMalloc(&ctx->d_error, 4)) != cudaSuccess) return bail(cudaGetErrorString(e));
   cudaMemset(ctx->d_error, 0, 4);
-  if((e = fused_dmma_configure((size_t) ctx->prop.sharedMemPerBlockOptin - 2048)) != cudaSuccess ||
-     (e = fused_dmma2_configure((size_t) ctx->prop.sharedMemPerBlockOptin - 2048)) != cudaSuccess)
+  if((e = fused_dmma_configure((size_t) ctx->prop.sharedMemPerBlockOptin - 2048)) != cudaSuccess)
     return bail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
@@ -776,7 +812,7 @@ int ccsdt_set_options(ccsdt_ctx* ctx, const ccsdt_options* o) {
     prod *= n.sub[i];
   }
   if(prod > 3) return ctx->fail("options.sub product must be <= 3 (at most 12 consumer warps)");
-  if(n.kernel != CCSDT_KERNEL_DMMA && n.kernel != CCSDT_KERNEL_SIMPLE && n.kernel != CCSDT_KERNEL_DMMA_WS)
+  if(n.kernel != CCSDT_KERNEL_DMMA && n.kernel != CCSDT_KERNEL_SIMPLE)
     return ctx->fail("unknown kernel id");
   if(n.nranks < 1) n.nranks = 1;
   if(n.rank < 0 || n.rank >= n.nranks) return ctx->fail("rank out of range");
@@ -928,6 +964,12 @@ int ccsdt_set_synthetic(ccsdt_ctx* ctx, uint64_t seed) {
   return 0;
 }
 
+int ccsdt_set_task_counter(ccsdt_ctx* ctx, int64_t* counter) {
+  if(!ctx) return 1;
+  ctx->task_counter = counter;
+  return 0;
+}
+
 int ccsdt_run(ccsdt_ctx* ctx, int64_t task_begin, int64_t task_end, double energies[2], double* per_task,
               ccsdt_stats* stats_out) {
   if(!ctx || !energies) return 1;
@@ -945,32 +987,53 @@ int ccsdt_run(ccsdt_ctx* ctx, int64_t task_begin, int64_t task_end, double energ
   (void) h2d0; (void) fetched0;
   energies[0] = energies[1] = 0.0;
 
-  std::vector<int64_t> mine;
-  for(int64_t i = task_begin; i < task_end; i++)
-    if(ctx->owner.empty() || ctx->owner[i] == ctx->opt.rank) mine.push_back(i);
+  // Task hand-out.  Static: the tasks the cost-balanced split gave this rank, in canonical order.
+  // Dynamic (a process-shared counter was set): every rank walks the SAME list, the tasks of the range in
+  // descending cost order, and claims the next unclaimed entry with one atomic fetch-add -- the role of
+  // the reference's AtomicCounterGA (ccsd_t_fused_driver.hpp:169-172, 456), with longest-task-first order.
+  std::vector<int64_t> mine, order;
+  if(ctx->task_counter) {
+    for(int64_t i = task_begin; i < task_end; i++) order.push_back(i);
+    std::vector<long double> cost(ctx->tasks.size());
+    for(int64_t i = task_begin; i < task_end; i++) cost[i] = task_ops(ctx->sp, ctx->tasks[i]);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cost[a] > cost[b]; });
+  }
+  else {
+    for(int64_t i = task_begin; i < task_end; i++)
+      if(ctx->owner.empty() || ctx->owner[i] == ctx->opt.rank) order.push_back(i);
+  }
+  int64_t cursor = 0;
+  auto    next_task = [&]() -> int64_t {
+    const int64_t k = ctx->task_counter ? __atomic_fetch_add(ctx->task_counter, (int64_t) 1, __ATOMIC_RELAXED) : cursor++;
+    return k < (int64_t) order.size() ? order[k] : -1;
+  };
   if(per_task) std::fill(per_task, per_task + 2 * (task_end - task_begin), 0.0);
 
-  if(!mine.empty()) {
+  if(!order.empty()) {
     if(int rc = ensure_pools(ctx)) return rc;
-    const int64_t n = (int64_t) mine.size();
-    if(n > ctx->task_energy_cap) {
+    const int64_t cap = (int64_t) order.size();
+    if(cap > ctx->task_energy_cap) {
       if(ctx->d_task_energy) CK(cudaFree(ctx->d_task_energy));
-      ctx->task_energy_cap = n + 16;
+      ctx->task_energy_cap = cap + 16;
       CK(cudaMalloc(&ctx->d_task_energy, (size_t) ctx->task_energy_cap * 16));
     }
     CK(cudaMemsetAsync(ctx->d_error, 0, 4, ctx->s_compute));
     const int nbuf = ctx->opt.overlap ? 2 : 1;
-    for(int64_t j = 0; j < n; j++) {
+    for(int64_t j = 0;; j++) {
+      const int64_t ti = next_task();
+      if(ti < 0) break;
+      mine.push_back(ti);
       StageBuf& b = ctx->buf[j % nbuf];
       // the buffer's previous task must have finished computing before its panels are rebuilt
       if(b.timing_pending) {
         if(int rc = collect_timing(ctx, b)) return rc;
       }
       CK(cudaStreamWaitEvent(ctx->s_stage, b.done, 0));
-      if(int rc = stage_task(ctx, b, ctx->tasks[mine[j]])) return rc;
+      if(int rc = stage_task(ctx, b, ctx->tasks[ti])) return rc;
       if(int rc = launch_task(ctx, b, j)) return rc;
-      ctx->stats.counted_flops += (double) task_ops(ctx->sp, ctx->tasks[mine[j]]);
+      ctx->stats.counted_flops += (double) task_ops(ctx->sp, ctx->tasks[ti]);
     }
+    const int64_t n = (int64_t) mine.size();
     for(int i = 0; i < nbuf; i++)
       if(int rc = collect_timing(ctx, ctx->buf[i])) return rc;
     cudaError_t e = cudaStreamSynchronize(ctx->s_compute);
@@ -982,13 +1045,18 @@ int ccsdt_run(ccsdt_ctx* ctx, int64_t task_begin, int64_t task_end, double energ
     uint32_t flag = 0;
     CK(cudaMemcpy(&flag, ctx->d_error, 4, cudaMemcpyDeviceToHost));
     if(flag) return ctx->fail("device error flag " + std::to_string(flag), 9);
-    std::vector<double> e_host((size_t) 2 * n);
-    CK(cudaMemcpy(e_host.data(), ctx->d_task_energy, (size_t) n * 16, cudaMemcpyDeviceToHost));
+    std::vector<double> e_host((size_t) 2 * std::max<int64_t>(n, 1));
+    if(n) CK(cudaMemcpy(e_host.data(), ctx->d_task_energy, (size_t) n * 16, cudaMemcpyDeviceToHost));
     ctx->stats.d2h_bytes += n * 16;
-    // reduction order: boxes in box-id order inside a task (fixed tree), tasks in canonical task order
-    for(int64_t j = 0; j < n; j++) {
-      const double f  = ctx->tasks[mine[j]].factor;
-      const double e1 = f * e_host[2 * j], e2 = f * e_host[2 * j + 1];
+    // reduction order: boxes in box-id order inside a task (fixed tree), then this rank's tasks in
+    // canonical task order (whatever order they were claimed in)
+    std::vector<int64_t> slot_of(n);
+    for(int64_t j = 0; j < n; j++) slot_of[j] = j;
+    std::sort(slot_of.begin(), slot_of.end(), [&](int64_t a, int64_t b) { return mine[a] < mine[b]; });
+    for(int64_t jj = 0; jj < n; jj++) {
+      const int64_t j  = slot_of[jj];
+      const double  f  = ctx->tasks[mine[j]].factor;
+      const double  e1 = f * e_host[2 * j], e2 = f * e_host[2 * j + 1];
       energies[0] += e1;
       energies[1] += e2;
       if(per_task) {

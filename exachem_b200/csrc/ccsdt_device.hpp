@@ -72,8 +72,15 @@ struct alignas(64) TaskParams {
   int32_t     ns1;
   S1Dev       s1[9];
   const double* evl[6]; // orbital-energy slices of the six tiles
-  double*     partial;  // [nboxes][2] per-box energy partials
-  int32_t     nboxes;
+  double*     partial;  // [nboxes_padded][2] per-box energy partials (zero for ids that are not boxes)
+  int32_t     nboxes;   // boxes of the tile
+  // Box ids are handed out in brick-major order: a brick is a (brick[0..5])-shaped group of boxes that
+  // is as close to a 6-d cube (in elements) as the tile allows, so that the boxes in flight at any
+  // time share operand rows under all 18 index groupings (L2 reuse).  ids run over the padded grid
+  // nbrick*brick; ids whose coordinates fall outside nbox are skipped by the scheduler.
+  int32_t     brick[6], nbrick[6];
+  int32_t     nboxes_padded;
+  uint32_t*   box_counter; // dynamic box scheduler: next id, zeroed before every launch
   int32_t     stages, stage_bytes;
   uint32_t*   error_flag;
 };
@@ -104,8 +111,6 @@ cudaError_t launch_fused_dmma(const TaskParams& p, int grid, int consumer_warps,
 cudaError_t launch_fused_simple(const TaskParams& p, cudaStream_t st, int* grid_out);
 cudaError_t launch_reduce_partials(const double* partial, int n, double* out2, cudaStream_t st);
 cudaError_t fused_dmma_configure(size_t smem_bytes);
-cudaError_t fused_dmma2_configure(size_t smem_bytes);
-cudaError_t launch_fused_dmma2(const TaskParams& p, int grid, int warps, size_t smem_bytes, cudaStream_t st);
 int         fused_dmma_max_ctas_per_sm(int threads, size_t smem_bytes);
 
 cudaError_t probe_fp64_peak(int use_dmma, int iters, double* tflops, double* ms);

@@ -1,4 +1,4 @@
-// Device helpers shared by the fused kernels (ccsdt_kernels.cu, ccsdt_fused2.cu).
+// Device helpers shared by the fused kernels (ccsdt_kernels.cu).
 #pragma once
 #include "ccsdt_device.hpp"
 
@@ -90,19 +90,27 @@ struct BoxCoord {
   int off[6]; // element offset of the box inside the tile, per index id
 };
 
-__device__ __forceinline__ BoxCoord decode_box(const TaskParams& p, int box) {
-  // h3 fastest ... p4 slowest: consecutive (co-resident) boxes share most operand rows
-  BoxCoord b;
-  int      r = box;
-  int      q;
-  q = r % p.nbox[2]; r /= p.nbox[2]; b.off[2] = q * p.c[2];
-  q = r % p.nbox[1]; r /= p.nbox[1]; b.off[1] = q * p.c[1];
-  q = r % p.nbox[0]; r /= p.nbox[0]; b.off[0] = q * p.c[0];
-  q = r % p.nbox[5]; r /= p.nbox[5]; b.off[5] = q * PBOX;
-  q = r % p.nbox[4]; r /= p.nbox[4]; b.off[4] = q * PBOX;
-  b.off[3] = r * PBOX;
-  return b;
+// id -> box coordinates; false when the id is padding of the brick grid.  Inside a brick and across
+// bricks h3 runs fastest, then h2, h1, p6, p5, p4.
+__device__ __forceinline__ bool decode_box(const TaskParams& p, int id, BoxCoord& b) {
+  const int order[6] = {2, 1, 0, 5, 4, 3};
+  int       in[6], r = id;
+  bool      valid = true;
+#pragma unroll
+  for(int i = 0; i < 6; i++) {
+    const int d = order[i];
+    in[d]       = r % p.brick[d];
+    r /= p.brick[d];
+  }
+#pragma unroll
+  for(int i = 0; i < 6; i++) {
+    const int d  = order[i];
+    const int bi = (r % p.nbrick[d]) * p.brick[d] + in[d];
+    r /= p.nbrick[d];
+    valid &= bi < p.nbox[d];
+    b.off[d] = bi * (d < 3 ? p.c[d] : PBOX);
+  }
+  return valid;
 }
-
 
 } // namespace ccsdt

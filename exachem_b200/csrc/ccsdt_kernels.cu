@@ -257,6 +257,18 @@ __device__ __forceinline__ void produce_term(const TaskParams& p, const TermDev&
   }
 }
 
+// Box queue: the producer warp owns the dynamic box scheduler (one atomicAdd per box on a global
+// counter, ids in brick-major order) and tells the consumers which box the slabs it is about to issue
+// belong to.  Every box has the same number of slabs, so the consumers only need the coordinates for
+// the epilogue.  Entry seq % BOXQ is written before the first slab of box number seq is issued and is
+// published by that slab's mbarrier completion; the producer is never more than `stages` slabs (hence
+// boxes) ahead, so MAX_STAGES + 2 entries cannot be overrun.  id < 0 ends the CTA.
+constexpr int BOXQ = MAX_STAGES + 2;
+struct BoxQueueEntry {
+  int      id;
+  BoxCoord bc;
+};
+
 // blockDim.x = 32 * (consumer_warps + 1); the last warp is the TMA producer.
 // Two instantiations: <160,3> (4 consumer warps, three CTAs per SM) and <416,1> (8 or 12 consumer
 // warps, one CTA per SM); both get the full 128 registers per thread, which the 64 accumulator
@@ -265,7 +277,8 @@ template<int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_constant__ TaskParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES];
-  __shared__ double red[2][16];
+  __shared__ double        red[2][16];
+  __shared__ BoxQueueEntry boxq[BOXQ];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncw = (int) (blockDim.x >> 5) - 1; // consumer warps
@@ -292,8 +305,29 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
 
   if(warp == ncw) {
     // ================= producer warp =================
-    for(int box = blockIdx.x; box < p.nboxes; box += gridDim.x) {
-      const BoxCoord bc = decode_box(p, box);
+    for(int seq = 0;; seq++) {
+      int      id = -1;
+      BoxCoord bc;
+      if(lane == 0) {
+        for(;;) {
+          id = (int) atomicAdd(p.box_counter, 1u);
+          if(id >= p.nboxes_padded) {
+            id = -1;
+            break;
+          }
+          if(decode_box(p, id, bc)) break;
+        }
+        BoxQueueEntry& e = boxq[seq % BOXQ];
+        e.id             = id;
+        e.bc             = bc;
+        if(id < 0) {
+          // end marker: complete one more phase of the next full barrier without data
+          mbar_wait(empty_bar + 8 * ring.stage, ring.phase ^ 1u, p.error_flag, 2);
+          mbar_arrive(full_bar + 8 * ring.stage);
+        }
+      }
+      id = __shfl_sync(0xffffffffu, id, 0);
+      if(id < 0) break;
       if(lane == 0)
         for(int t = 0; t < p.nterms_x; t++) produce_term(p, p.term[t], bc, ring, ring_base, full_bar, empty_bar);
       __syncwarp(); // reconverge before the CTA-wide (aligned) barriers
@@ -320,8 +354,12 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
   const int q6  = frag_row(lane >> 2);            // particle offset of this lane's DMMA row
   const int qc0 = frag_row(2 * l3);               // particle offset of DMMA column 2*l3 (+2 for column 2*l3+1)
 
-  for(int box = blockIdx.x; box < p.nboxes; box += gridDim.x) {
-    const BoxCoord bc = decode_box(p, box);
+  for(int seq = 0;; seq++) {
+    // the first slab of the box publishes its queue entry
+    mbar_wait(full_bar + 8 * ring.stage, ring.phase, p.error_flag, 4);
+    const int box = boxq[seq % BOXQ].id;
+    if(box < 0) break;
+    const BoxCoord bc = boxq[seq % BOXQ].bc;
     double         acc[32];
 #pragma unroll
     for(int i = 0; i < 32; i++) acc[i] = 0.0;
@@ -468,19 +506,26 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
   }
 }
 
+// <160,3>: 4+1 warps, three CTAs per SM at 128 registers; <288,1>: 8+1 warps, one CTA per SM with up to
+// 224 registers (no spills); <416,1>: 12+1 warps, one CTA per SM at 152 registers.
 cudaError_t fused_dmma_configure(size_t smem_bytes) {
-  cudaError_t e = cudaFuncSetAttribute(fused_t_dmma_kernel<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int) smem_bytes);
-  if(e != cudaSuccess) return e;
+  cudaError_t e;
+  if((e = cudaFuncSetAttribute(fused_t_dmma_kernel<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int) smem_bytes)) != cudaSuccess)
+    return e;
+  if((e = cudaFuncSetAttribute(fused_t_dmma_kernel<288, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int) smem_bytes)) != cudaSuccess)
+    return e;
   return cudaFuncSetAttribute(fused_t_dmma_kernel<416, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int) smem_bytes);
 }
 
 int fused_dmma_max_ctas_per_sm(int threads, size_t smem_bytes) {
   int         n = 0;
-  cudaError_t e = threads <= 160
-                    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_t_dmma_kernel<160, 3>, threads, smem_bytes)
-                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_t_dmma_kernel<416, 1>, threads, smem_bytes);
+  cudaError_t e =
+    threads <= 160   ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_t_dmma_kernel<160, 3>, threads, smem_bytes)
+    : threads <= 288 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_t_dmma_kernel<288, 1>, threads, smem_bytes)
+                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fused_t_dmma_kernel<416, 1>, threads, smem_bytes);
   return e == cudaSuccess ? n : 0;
 }
 
@@ -488,6 +533,7 @@ cudaError_t launch_fused_dmma(const TaskParams& p, int grid, int consumer_warps,
                               cudaStream_t st) {
   const int threads = 32 * (consumer_warps + 1);
   if(threads <= 160) fused_t_dmma_kernel<160, 3><<<grid, threads, smem_bytes, st>>>(p);
+  else if(threads <= 288) fused_t_dmma_kernel<288, 1><<<grid, threads, smem_bytes, st>>>(p);
   else if(threads <= 416) fused_t_dmma_kernel<416, 1><<<grid, threads, smem_bytes, st>>>(p);
   else return cudaErrorInvalidConfiguration;
   return cudaGetLastError();

@@ -23,7 +23,7 @@ from . import _lib
 from ._lib import FETCH_FN, Options, Stats
 
 T1, T2, V_IJAB, V_IJKA, V_IABC = 0, 1, 2, 3, 4
-KERNEL_DMMA, KERNEL_SIMPLE, KERNEL_DMMA_WS = 0, 1, 2
+KERNEL_DMMA, KERNEL_SIMPLE = 0, 1
 
 
 class CcsdtError(RuntimeError):
@@ -203,6 +203,10 @@ class Context:
 
     def set_synthetic(self, seed: int):
         self._ck(self.L.ccsdt_set_synthetic(self.h, seed))
+
+    def set_task_counter(self, address: int | None):
+        """address of a process-shared int64 (see multigpu.SharedTaskCounter); None = static split."""
+        self._ck(self.L.ccsdt_set_task_counter(self.h, C.c_void_p(address) if address else None))
 
     def run(self, task_begin=0, task_end=-1, per_task_n=0):
         e = np.zeros(2)

@@ -23,6 +23,7 @@
  *                           ccsd_t_all_fused.hpp:77-286 + the kernel launcher ccsd_t_all_fused_gpu.cu:2571
  *                           + hostEnergyReduce ccsd_t_all_fused.hpp:19-32; returns the rank-partial
  *                           (energy1 = E[T], energy2 = E(T)) the caller reduces at ccsd_t.cpp:262-263
+ *   ccsdt_set_task_counter <- AtomicCounterGA (allocate / fetch_add / deallocate) ccsd_t_fused_driver.hpp:169-172,456,541
  *   ccsdt_check_memory   <- check_memory_req                 exachem/cc/ccsd_t/hybrid.cpp:19-41
  *
  * Conventions: plain pointers and sizes, no C++ or torch types.  Every function returns 0 on success
@@ -62,9 +63,9 @@ enum {
   CCSDT_V_IABC = 4  /* v2iabc [O][V][V][V]    */
 };
 
-/* DMMA: the product kernel (all warps issue DMMA, warp 0 pumps the TMA ring); DMMA_WS: first-generation
- * variant with a dedicated TMA producer warp; SIMPLE: diagnostic one-thread-per-element FMA kernel */
-enum { CCSDT_KERNEL_DMMA = 0, CCSDT_KERNEL_SIMPLE = 1, CCSDT_KERNEL_DMMA_WS = 2 };
+/* DMMA: the product kernel (TMA producer warp + FP64 DMMA consumer warps); SIMPLE: diagnostic
+ * one-thread-per-element FMA kernel over the same staged panels */
+enum { CCSDT_KERNEL_DMMA = 0, CCSDT_KERNEL_SIMPLE = 1 };
 
 typedef struct ccsdt_options {
   int32_t kernel;        /* CCSDT_KERNEL_DMMA (product) or CCSDT_KERNEL_SIMPLE (diagnostic FMA kernel) */
@@ -121,6 +122,13 @@ CCSDT_API int ccsdt_put_dense(ccsdt_ctx* ctx, int tensor, const double* host_den
 CCSDT_API int ccsdt_put_block(ccsdt_ctx* ctx, int tensor, const uint32_t bid[4], const double* host_block);
 CCSDT_API int ccsdt_set_fetch(ccsdt_ctx* ctx, ccsdt_fetch_fn fn, void* user);
 CCSDT_API int ccsdt_set_synthetic(ccsdt_ctx* ctx, uint64_t seed); /* procedural tensors generated on the device */
+
+/* Dynamic task hand-out across ranks: `counter` points to an int64 in memory shared by all ranks of the
+ * node (POSIX/SysV shared memory, an MPI shared window, ...), zeroed before every ccsdt_run by one rank
+ * with a barrier on both sides.  Each rank then claims tasks of the range in descending-cost order with
+ * one atomic fetch-add per task (replaces AtomicCounterGA, ccsd_t_fused_driver.hpp:169-172,456).
+ * NULL (default) = the static cost-balanced split selected by options.rank / options.nranks. */
+CCSDT_API int ccsdt_set_task_counter(ccsdt_ctx* ctx, int64_t* counter);
 
 /* runs kernel tasks [task_begin, task_end) of the canonical list that belong to this rank
  * (task_end < 0 = to the end).  energies[0] = E[T] partial, energies[1] = E(T) partial, both already
