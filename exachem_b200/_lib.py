@@ -18,7 +18,7 @@ _u8p = C.POINTER(C.c_uint8)
 class Options(C.Structure):
     _fields_ = [("kernel", C.c_int32), ("sub", C.c_int32 * 3), ("stages", C.c_int32),
                 ("ctas_per_sm", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
-                ("overlap", C.c_int32), ("verbose", C.c_int32)]
+                ("overlap", C.c_int32), ("stagger", C.c_int32), ("verbose", C.c_int32)]
 
 
 class Stats(C.Structure):

@@ -230,7 +230,7 @@ int ensure_pools(ccsdt_ctx* ctx) {
     b.desc_cap = 64 + 9 * 2 * 2 * (sp.noab() + sp.nvab() + 2);
     CK(cudaMalloc(&b.d_descs, sizeof(GatherDesc) * b.desc_cap));
     CK(cudaMallocHost(&b.h_descs, sizeof(GatherDesc) * b.desc_cap));
-    CK(cudaMalloc(&b.d_counter, 4));
+    CK(cudaMalloc(&b.d_counter, 4 * COUNTER_WORDS));
     if(int rc = make_tmaps(ctx, b)) return rc;
     if(!b.staged) {
       CK(cudaEventCreateWithFlags(&b.staged, cudaEventDisableTiming));
@@ -568,6 +568,8 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     memset(&sd, 0, sizeof(sd));
     sd.a        = pa;
     sd.b        = pb;
+    sd.hx       = T.hx;
+    sd.pa       = T.pa;
     sd.sa[T.hx] = g.TPp;
     sd.sa[T.pa] = 1;
     sd.sb[T.pb] = g.TPp * g.THp * g.THp;
@@ -648,6 +650,14 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     if(padded > 0x7fffffff) return ctx->fail("task has too many CTA boxes", 7);
     P.nboxes_padded = (int) padded;
     P.box_counter   = b.d_counter;
+    // one box keeps the tensor pipe of an SM busy for (k-steps x 16 DMMA x 16 cycles) / 4 sub-partitions x
+    // 4 warps = k-steps x 256 cycles; co-resident CTAs start that far apart (options.stagger, default on)
+    int64_t ksteps = 0;
+    for(int t = 0; t < P.nterms; t++) ksteps += (int64_t) (P.term[t].kslabs - 1) * 4 + P.term[t].ksteps_last;
+    P.ctas_per_sm    = ctas;
+    P.stagger_cycles = (ctas > 1 && ctx->opt.stagger && nboxes >= 4 * in_flight)
+                         ? (int) std::min<int64_t>(ksteps * 256 + 8192, 50000000)
+                         : 0;
     need_partial    = padded;
   }
   b.nparts = need_partial;
@@ -695,7 +705,7 @@ int launch_task(ccsdt_ctx* ctx, StageBuf& b, int64_t slot) {
   else {
     // ids of the padded brick grid that are not boxes are never written: their partials stay zero
     CK(cudaMemsetAsync(b.d_partial, 0, (size_t) b.nparts * 16, ctx->s_compute));
-    CK(cudaMemsetAsync(b.d_counter, 0, 4, ctx->s_compute));
+    CK(cudaMemsetAsync(b.d_counter, 0, 4 * COUNTER_WORDS, ctx->s_compute));
     CK(cudaEventRecord(b.k0, ctx->s_compute));
     CK(launch_fused_dmma(b.params, b.grid, b.consumer_warps, b.smem, ctx->s_compute));
     CK(cudaEventRecord(b.k1, ctx->s_compute));
@@ -732,9 +742,10 @@ int ccsdt_default_options(ccsdt_options* o) {
   if(!o) return 1;
   memset(o, 0, sizeof(*o));
   o->kernel = CCSDT_KERNEL_DMMA;
-  o->sub[0] = 1, o->sub[1] = 1, o->sub[2] = 2;
+  o->sub[0] = 1, o->sub[1] = 1, o->sub[2] = 1;
   o->nranks  = 1;
   o->overlap = 1;
+  o->stagger = 1;
   return 0;
 }
 
@@ -805,7 +816,7 @@ int ccsdt_destroy(ccsdt_ctx* ctx) {
 int ccsdt_set_options(ccsdt_ctx* ctx, const ccsdt_options* o) {
   if(!ctx || !o) return 1;
   ccsdt_options n = *o;
-  if(n.sub[0] == 0 && n.sub[1] == 0 && n.sub[2] == 0) n.sub[0] = 1, n.sub[1] = 1, n.sub[2] = 2;
+  if(n.sub[0] == 0 && n.sub[1] == 0 && n.sub[2] == 0) n.sub[0] = 1, n.sub[1] = 1, n.sub[2] = 1;
   int prod = 1;
   for(int i = 0; i < 3; i++) {
     if(n.sub[i] < 1 || n.sub[i] > 3) return ctx->fail("options.sub entries must be 1, 2 or 3");

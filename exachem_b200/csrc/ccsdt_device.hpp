@@ -20,6 +20,7 @@ constexpr int ROW_BYTES  = 128; // KSLAB * 8
 constexpr int PBOX       = 8;   // particle extent of a CTA box (= DMMA m and n)
 constexpr int MAX_TERMS  = 18;
 constexpr int MAX_STAGES = 8;
+constexpr int COUNTER_WORDS = 1 + 256; // box counter + per-SM start counters
 
 struct PoolGeom {
   int     THp, TPp; // padded max hole / particle tile extent (multiples of 4 / 8)
@@ -58,6 +59,7 @@ struct S1Dev {
   const double* a;
   const double* b;
   int32_t       sa[6], sb[6]; // element strides per index id (0 where the operand lacks the index)
+  int32_t       hx, pa;       // index ids of the two indices a carries (hole 0..2, particle 3..5)
 };
 
 struct alignas(64) TaskParams {
@@ -80,7 +82,10 @@ struct alignas(64) TaskParams {
   // nbrick*brick; ids whose coordinates fall outside nbox are skipped by the scheduler.
   int32_t     brick[6], nbrick[6];
   int32_t     nboxes_padded;
-  uint32_t*   box_counter; // dynamic box scheduler: next id, zeroed before every launch
+  uint32_t*   box_counter; // dynamic box scheduler: [0] = next id, [1 + smid] = CTAs that started on that SM;
+                           // zeroed before every launch
+  int32_t     stagger_cycles; // start delay per co-resident CTA slot (de-phases the epilogues of the CTAs of an SM)
+  int32_t     ctas_per_sm;
   int32_t     stages, stage_bytes;
   uint32_t*   error_flag;
 };

@@ -32,9 +32,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                : "memory");
   return ok != 0;
 }
-// bounded wait: a pipeline bug must end in a trap (reported as a CUDA error), never in a hung GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* error_flag, int tag) {
-  if(mbar_try_wait(bar, parity)) return;
+// bounded wait: a pipeline bug must end in a trap (reported as a CUDA error), never in a hung GPU.
+// The slow path is kept out of line: the wait is inlined at every pipeline step and the kernel's hot
+// code has to stay small (instruction cache).
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t* error_flag, int tag) {
   const long long t0 = clock64();
   while(!mbar_try_wait(bar, parity)) {
     if(clock64() - t0 > 4000000000ll) { // ~2 s
@@ -43,6 +44,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t* error_flag, int tag) {
+  if(!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, error_flag, tag);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
                                             int c1, int c2, int c3) {

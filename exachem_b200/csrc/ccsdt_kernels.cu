@@ -15,6 +15,7 @@
 #include "ccsdt_kernel_common.cuh"
 
 #include <cstdio>
+#include <type_traits>
 
 namespace ccsdt {
 
@@ -77,6 +78,48 @@ __device__ __forceinline__ double s1_sum(const TaskParams& p, const int coord[6]
     s += __ldg(t.a + oa) * __ldg(t.b + ob);
   }
   return s;
+}
+
+// d / D for the energy denominators (|D| is an orbital-energy gap, far from 0, inf and the subnormals):
+// hardware reciprocal seed (2^-23), two Newton steps, one correction of the quotient.  Within 1 ulp of
+// the IEEE quotient; replaces the ~30-instruction generic FP64 division, 32 of which sat in the epilogue.
+__device__ __forceinline__ double div_fast(double d, double D) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(D));
+  double e = fma(-D, r, 1.0);
+  r        = fma(r, e, r);
+  e        = fma(-D, r, 1.0);
+  r        = fma(r, e, r);
+  double q = d * r;
+  return fma(fma(-D, q, d), r, q);
+}
+
+// One s1 term of a thread's 32 elements: sum_e tq[e] * a[e] * b[e] with a = sign*T1[pa,hx] and
+// b = v2ijab[hz,hy,pc,pb].  Element bit <-> accumulator index: bit 4 = i1, 3 = i2, 2 = i3, 1 = ql, 0 = r.
+// a carries exactly one hole (HX, compile time) and at most one of the two in-thread particle bits; b
+// carries the other two holes and the remaining particle bits.  Absent indices have stride 0, so
+// 8 loads of a and 16 of b (some of them repeats that hit L1) serve all 32 elements; only three
+// instantiations exist (code size: the epilogue shares the instruction cache with the DMMA loops).
+template<int HX>
+__device__ __forceinline__ double s1_term(const double (&tq)[32], const double* __restrict__ pa,
+                                          const double* __restrict__ pb, const int (&da)[5], const int (&db)[5]) {
+  constexpr int HB = 4 - HX;                           // element bit of a's hole
+  constexpr int O1 = HX == 0 ? 3 : 4, O2 = HX == 2 ? 3 : 2; // element bits of the other two holes
+  double        av[2][4], bv[4][4];
+#pragma unroll
+  for(int h = 0; h < 2; h++)
+#pragma unroll
+    for(int q = 0; q < 4; q++) av[h][q] = __ldg(pa + h * da[HB] + (q >> 1) * da[1] + (q & 1) * da[0]);
+#pragma unroll
+  for(int o = 0; o < 4; o++)
+#pragma unroll
+    for(int q = 0; q < 4; q++)
+      bv[o][q] = __ldg(pb + (o >> 1) * db[O1] + (o & 1) * db[O2] + (q >> 1) * db[1] + (q & 1) * db[0]);
+  double sum = 0.0;
+#pragma unroll
+  for(int e = 0; e < 32; e++)
+    sum += tq[e] * (av[(e >> HB) & 1][e & 3] * bv[(((e >> O1) & 1) << 1) | ((e >> O2) & 1)][e & 3]);
+  return sum;
 }
 
 // =================================================================================================
@@ -144,6 +187,9 @@ cudaError_t launch_fused_simple(const TaskParams& p, cudaStream_t st, int* grid_
 // =================================================================================================
 // the fused DMMA kernel
 // =================================================================================================
+template<int N>
+using Int = std::integral_constant<int, N>;
+
 // All K slabs of one contraction for one consumer warp.
 // acc index = (((i1*2 + i2)*2 + i3)*2 + ql)*2 + r  with i* the hole offsets inside the warp group's
 // (2,2,2) sub-box, ql the warp's tile-particle slot and r the DMMA column parity.
@@ -176,41 +222,60 @@ __device__ __forceinline__ void consume_term(double (&acc)[32], const TaskParams
       hhp_off[ia][ib] =
         (uint32_t) ((hpp_rows + ((sub_off[HA] + ia) * c_o1 + sub_off[HB] + ib) * 8) * ROW_BYTES) + lane_const;
 
+  // One 4-wide k-step = 16 DMMAs from 4 HPP fragments (fh) and 4 HHP fragments (fg), all single-buffered:
+  // the DMMAs run fh-major, each fh is re-requested for the next step right after its fourth and last use,
+  // each fg after its last use in the final group -- every reload sits at least three DMMA issue slots
+  // (~48 cycles) ahead of its first use, which covers the shared-memory latency.  The k-loop is NOT
+  // unrolled: the six (HH, A_HPP) instantiations of this loop are the whole hot code of the kernel and must
+  // stay resident in the instruction cache while co-resident CTAs run different terms.
+  // Loads past the end of the term read valid but unused shared memory (no conditional loads).
+  double fh[2][2], fg[2][2];
+  mbar_wait(full_bar + 8 * ring.stage, ring.phase, p.error_flag, 1);
+  uint32_t base = ring_base + ring.stage * (uint32_t) p.stage_bytes;
+#pragma unroll
+  for(int x = 0; x < 2; x++)
+#pragma unroll
+    for(int y = 0; y < 2; y++) {
+      fh[x][y] = lds_f64(base + (jx << 5) + hpp_off[x][y]);
+      fg[x][y] = lds_f64(base + (jx << 5) + hhp_off[x][y]);
+    }
+
   for(int s = 0; s < td.kslabs; s++) {
-    mbar_wait(full_bar + 8 * ring.stage, ring.phase, p.error_flag, 1);
-    const uint32_t base = ring_base + ring.stage * (uint32_t) p.stage_bytes;
-    const uint32_t nj   = (s == td.kslabs - 1) ? (uint32_t) td.ksteps_last : 4u; // K tail: 4-wide steps only
+    const bool     last = s == td.kslabs - 1;
+    const uint32_t nj   = last ? (uint32_t) td.ksteps_last : 4u; // K tail: 4-wide steps only
+    Ring           nxt  = ring;
+    nxt.advance((uint32_t) p.stages);
+    const uint32_t next_base = last ? base : ring_base + nxt.stage * (uint32_t) p.stage_bytes;
+#pragma unroll 1
+    for(uint32_t j = 0; j < nj; j++) {
+      uint32_t jn; // shared-memory address (without fragment offset) of the next step's fragments
+      if(j == 3) {
+        if(!last) mbar_wait(full_bar + 8 * nxt.stage, nxt.phase, p.error_flag, 1);
+        jn = next_base + (jx << 5);
+      }
+      else jn = base + (((j + 1) ^ jx) << 5);
 #pragma unroll
-    for(uint32_t j = 0; j < 4; j++) {
-      if(j >= nj) break;
-      const uint32_t jo = base + ((j ^ jx) << 5);
-      double         fh[2][2], fg[2][2];
+      for(int hx = 0; hx < 2; hx++)
 #pragma unroll
-      for(int x = 0; x < 2; x++)
+        for(int ql = 0; ql < 2; ql++) {
 #pragma unroll
-        for(int y = 0; y < 2; y++) {
-          fh[x][y] = lds_f64(jo + hpp_off[x][y]);
-          fg[x][y] = lds_f64(jo + hhp_off[x][y]);
-        }
+          for(int ga = 0; ga < 2; ga++)
 #pragma unroll
-      for(int i1 = 0; i1 < 2; i1++)
-#pragma unroll
-        for(int i2 = 0; i2 < 2; i2++)
-#pragma unroll
-          for(int i3 = 0; i3 < 2; i3++)
-#pragma unroll
-            for(int ql = 0; ql < 2; ql++) {
-              const int    hi[3] = {i1, i2, i3};
-              const double vh    = fh[hi[HH]][ql];
-              const double vg    = fg[hi[HA]][hi[HB]];
-              const int    ai    = ((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2);
-              if(A_HPP) dmma884(acc[ai], acc[ai + 1], vh, vg);
-              else dmma884(acc[ai], acc[ai + 1], vg, vh);
+            for(int gb = 0; gb < 2; gb++) {
+              int hi[3];
+              hi[HH] = hx, hi[HA] = ga, hi[HB] = gb;
+              const int ai = ((((hi[0] * 2 + hi[1]) * 2 + hi[2]) * 2 + ql) * 2);
+              if(A_HPP) dmma884(acc[ai], acc[ai + 1], fh[hx][ql], fg[ga][gb]);
+              else dmma884(acc[ai], acc[ai + 1], fg[ga][gb], fh[hx][ql]);
+              if(hx == 1 && ql == 1) fg[ga][gb] = lds_f64(jn + hhp_off[ga][gb]);
             }
+          fh[hx][ql] = lds_f64(jn + hpp_off[hx][ql]);
+        }
     }
     __syncwarp();
     if(lane == 0) mbar_arrive(empty_bar + 8 * ring.stage);
-    ring.advance((uint32_t) p.stages);
+    ring = nxt;
+    base = next_base;
   }
 }
 
@@ -305,6 +370,18 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
 
   if(warp == ncw) {
     // ================= producer warp =================
+    // The CTAs that share an SM all take the same time per box; started together they would all reach
+    // their (tensor-pipe-idle) relayouts and epilogues at the same moment.  The k-th CTA to start on an SM
+    // therefore delays its first load by k/ctas_per_sm of a box time, so that one CTA's epilogue runs under
+    // the other CTAs' DMMAs.
+    if(lane == 0 && p.stagger_cycles > 0) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const uint32_t  slot = atomicAdd(p.box_counter + 1 + (smid & 255u), 1u) % (uint32_t) p.ctas_per_sm;
+      const long long t0   = clock64();
+      while(clock64() - t0 < (long long) slot * p.stagger_cycles) {}
+    }
+    __syncwarp();
     for(int seq = 0;; seq++) {
       int      id = -1;
       BoxCoord bc;
@@ -328,16 +405,15 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
       }
       id = __shfl_sync(0xffffffffu, id, 0);
       if(id < 0) break;
-      if(lane == 0)
-        for(int t = 0; t < p.nterms_x; t++) produce_term(p, p.term[t], bc, ring, ring_base, full_bar, empty_bar);
-      __syncwarp(); // reconverge before the CTA-wide (aligned) barriers
-      if(relayout) {
-        __syncthreads(); // consumers are done with every X slab: the ring is idle
-        __syncthreads(); // accumulators parked in the ring
-        __syncthreads(); // accumulators reloaded: the ring may be refilled
+      for(int t = 0; t < p.nterms; t++) {
+        if(relayout && t == p.nterms_x) {
+          __syncwarp();    // reconverge before the CTA-wide (aligned) barriers
+          __syncthreads(); // consumers are done with every X slab: the ring is idle
+          __syncthreads(); // accumulators parked in the ring
+          __syncthreads(); // accumulators reloaded: the ring may be refilled
+        }
+        if(lane == 0) produce_term(p, p.term[t], bc, ring, ring_base, full_bar, empty_bar);
       }
-      if(lane == 0)
-        for(int t = p.nterms_x; t < p.nterms; t++) produce_term(p, p.term[t], bc, ring, ring_base, full_bar, empty_bar);
       __syncwarp();
     }
     return;
@@ -364,50 +440,47 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
 #pragma unroll
     for(int i = 0; i < 32; i++) acc[i] = 0.0;
 
-    for(int t = 0; t < p.nterms_x; t++)
+    for(int t = 0; t < p.nterms; t++) {
+      if(relayout && t == p.nterms_x) {
+        // X -> Y: swap the roles of p4 and p5 (tile particle <-> DMMA column) through shared memory.
+        // scratch index = ((((h1*c2 + h2)*c3 + h3)*8 + p4)*8 + p5)*8 + p6  (box-local coordinates)
+        __syncthreads();
+        double* scratch = reinterpret_cast<double*>(smem_raw + (ring_base - smem_u32(smem_raw)));
+#pragma unroll
+        for(int i1 = 0; i1 < 2; i1++)
+#pragma unroll
+          for(int i2 = 0; i2 < 2; i2++)
+#pragma unroll
+            for(int i3 = 0; i3 < 2; i3++)
+#pragma unroll
+              for(int ql = 0; ql < 2; ql++)
+#pragma unroll
+                for(int r = 0; r < 2; r++) {
+                  const int hl = ((sub_off[0] + i1) * p.c[1] + sub_off[1] + i2) * p.c[2] + sub_off[2] + i3;
+                  const int p4 = 2 * wq + ql, p5 = qc0 + 2 * r;
+                  scratch[((hl * 8 + p4) * 8 + p5) * 8 + q6] = acc[((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2) + r];
+                }
+        __syncthreads();
+#pragma unroll
+        for(int i1 = 0; i1 < 2; i1++)
+#pragma unroll
+          for(int i2 = 0; i2 < 2; i2++)
+#pragma unroll
+            for(int i3 = 0; i3 < 2; i3++)
+#pragma unroll
+              for(int ql = 0; ql < 2; ql++)
+#pragma unroll
+                for(int r = 0; r < 2; r++) {
+                  const int hl = ((sub_off[0] + i1) * p.c[1] + sub_off[1] + i2) * p.c[2] + sub_off[2] + i3;
+                  const int p5 = 2 * wq + ql, p4 = qc0 + 2 * r;
+                  acc[((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2) + r] = scratch[((hl * 8 + p4) * 8 + p5) * 8 + q6];
+                }
+        // generic-proxy accesses to the ring must be ordered before the TMA (async proxy) refills it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+      }
       consume_dispatch(acc, p, p.term[t], ring, ring_base, full_bar, empty_bar, sub_off, wq, lane);
-
-    if(relayout) {
-      // X -> Y: swap the roles of p4 and p5 (tile particle <-> DMMA column) through shared memory.
-      // scratch index = ((((h1*c2 + h2)*c3 + h3)*8 + p4)*8 + p5)*8 + p6  (box-local coordinates)
-      __syncthreads();
-      double* scratch = reinterpret_cast<double*>(smem_raw + (ring_base - smem_u32(smem_raw)));
-#pragma unroll
-      for(int i1 = 0; i1 < 2; i1++)
-#pragma unroll
-        for(int i2 = 0; i2 < 2; i2++)
-#pragma unroll
-          for(int i3 = 0; i3 < 2; i3++)
-#pragma unroll
-            for(int ql = 0; ql < 2; ql++)
-#pragma unroll
-              for(int r = 0; r < 2; r++) {
-                const int hl = ((sub_off[0] + i1) * p.c[1] + sub_off[1] + i2) * p.c[2] + sub_off[2] + i3;
-                const int p4 = 2 * wq + ql, p5 = qc0 + 2 * r;
-                scratch[((hl * 8 + p4) * 8 + p5) * 8 + q6] = acc[((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2) + r];
-              }
-      __syncthreads();
-#pragma unroll
-      for(int i1 = 0; i1 < 2; i1++)
-#pragma unroll
-        for(int i2 = 0; i2 < 2; i2++)
-#pragma unroll
-          for(int i3 = 0; i3 < 2; i3++)
-#pragma unroll
-            for(int ql = 0; ql < 2; ql++)
-#pragma unroll
-              for(int r = 0; r < 2; r++) {
-                const int hl = ((sub_off[0] + i1) * p.c[1] + sub_off[1] + i2) * p.c[2] + sub_off[2] + i3;
-                const int p5 = 2 * wq + ql, p4 = qc0 + 2 * r;
-                acc[((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2) + r] = scratch[((hl * 8 + p4) * 8 + p5) * 8 + q6];
-              }
-      // generic-proxy accesses to the ring must be ordered before the TMA (async proxy) refills it
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
     }
-
-    for(int t = p.nterms_x; t < p.nterms; t++)
-      consume_dispatch(acc, p, p.term[t], ring, ring_base, full_bar, empty_bar, sub_off, wq, lane);
 
     // ---------------- epilogue: denominators, E[T], then the s1 part of E(T) ----------------
     // E[T] += d*d/D ; E(T) += d*(d+s)/D = E[T] part + (d/D)*s.  Pass 1 turns every accumulator into
@@ -458,7 +531,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
               const bool     ok   = ok6 && (vmask & need) == need;
               const double   d    = acc[ai];
               const double   D    = eh[0][i1] + eh[1][i2] + eh[2][i3] - et[ql] - ec[r] - e6;
-              const double   tq   = ok ? d / D : 0.0;
+              const double   tq   = ok ? div_fast(d, D) : 0.0;
               e1 += tq * d;
               acc[ai] = tq;
             }
@@ -469,25 +542,14 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
                                  ccq * sd.sa[id_qc] + c6 * sd.sa[5]);
       const double* pb = sd.b + (hc[0] * sd.sb[0] + hc[1] * sd.sb[1] + hc[2] * sd.sb[2] + tcq * sd.sb[id_qt] +
                                  ccq * sd.sb[id_qc] + c6 * sd.sb[5]);
-      const int da[5] = {sd.sa[0], sd.sa[1], sd.sa[2], sd.sa[id_qt], 2 * sd.sa[id_qc]};
-      const int db[5] = {sd.sb[0], sd.sb[1], sd.sb[2], sd.sb[id_qt], 2 * sd.sb[id_qc]};
-      double    acc_s = 0.0;
-#pragma unroll
-      for(int i1 = 0; i1 < 2; i1++)
-#pragma unroll
-        for(int i2 = 0; i2 < 2; i2++)
-#pragma unroll
-          for(int i3 = 0; i3 < 2; i3++)
-#pragma unroll
-            for(int ql = 0; ql < 2; ql++)
-#pragma unroll
-              for(int r = 0; r < 2; r++) {
-                const int ai = ((((i1 * 2 + i2) * 2 + i3) * 2 + ql) * 2) + r;
-                const int oa = i1 * da[0] + i2 * da[1] + i3 * da[2] + ql * da[3] + r * da[4];
-                const int ob = i1 * db[0] + i2 * db[1] + i3 * db[2] + ql * db[3] + r * db[4];
-                acc_s += acc[ai] * (__ldg(pa + oa) * __ldg(pb + ob));
-              }
-      e2 += acc_s;
+      // strides per in-thread element bit: bit 4 = i1, 3 = i2, 2 = i3, 1 = ql, 0 = r (= accumulator index)
+      const int da[5] = {2 * sd.sa[id_qc], sd.sa[id_qt], sd.sa[2], sd.sa[1], sd.sa[0]};
+      const int db[5] = {2 * sd.sb[id_qc], sd.sb[id_qt], sd.sb[2], sd.sb[1], sd.sb[0]};
+      switch(sd.hx) {
+        case 0: e2 += s1_term<0>(acc, pa, pb, da, db); break;
+        case 1: e2 += s1_term<1>(acc, pa, pb, da, db); break;
+        default: e2 += s1_term<2>(acc, pa, pb, da, db); break;
+      }
     }
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) {

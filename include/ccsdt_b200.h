@@ -70,11 +70,12 @@ enum { CCSDT_KERNEL_DMMA = 0, CCSDT_KERNEL_SIMPLE = 1 };
 typedef struct ccsdt_options {
   int32_t kernel;        /* CCSDT_KERNEL_DMMA (product) or CCSDT_KERNEL_SIMPLE (diagnostic FMA kernel) */
   int32_t sub[3];        /* CTA box = (2*sub[0], 2*sub[1], 2*sub[2], 8, 8, 8) over (h1,h2,h3,p4,p5,p6);
-                            each entry 1..3, product <= 3 (4, 8 or 12 DMMA warps + 1 TMA warp).  0 = default (1,1,2) */
+                            each entry 1..3, product <= 3 (4, 8 or 12 DMMA warps + 1 TMA warp).  0 = default (1,1,1) */
   int32_t stages;        /* TMA ring depth, 0 = as many as fit */
   int32_t ctas_per_sm;   /* 0 = default for the box */
   int32_t rank, nranks;  /* this process's share of the task list (static cost-balanced split) */
   int32_t overlap;       /* 1 = stage task n+1 while task n computes (default), 0 = serial */
+  int32_t stagger;       /* 1 = de-phase the CTAs sharing an SM by a fraction of a box time (default), 0 = off */
   int32_t verbose;
 } ccsdt_options;
 

@@ -11,8 +11,8 @@ def main():
     tasks, fac, _ = drv.enumerate_tasks(sp, True)
     idx = [int(x) for x in sys.argv[4:]] or [0, len(tasks) // 3, (2 * len(tasks)) // 3, len(tasks) - 1]
     evl = syn.Orbitals(no, no, nv, nv).orbital_energies()
-    configs = [dict(sub=(1, 1, 2)), dict(sub=(1, 1, 1)), dict(sub=(2, 1, 1)), dict(sub=(1, 2, 1)), dict(sub=(1, 1, 3)),
-               dict(sub=(1, 1, 2), stages=3), dict(sub=(1, 1, 1), ctas_per_sm=2)]
+    configs = [dict(sub=(1, 1, 1)), dict(sub=(1, 1, 1), stagger=0), dict(sub=(1, 1, 2)), dict(sub=(1, 1, 1), ctas_per_sm=2),
+               dict(sub=(1, 1, 1), ctas_per_sm=2, stagger=0)]
     if os.environ.get("SWEEP_CONFIGS"):
         configs = [dict(sub=tuple(int(x) for x in c.split(","))) for c in os.environ["SWEEP_CONFIGS"].split(";")]
     for cfg in configs:
