@@ -6,17 +6,19 @@
 
 A "step" is one complete pass of the hot path over the workload:
   N = 1 : BASELINE.json configs[1] -- the benzene cc-pVDZ shape (O=21, V=93 per spin,
-          ccsdt_tilesize 40 -> 28 kernel tasks, 1.59e13 counted flops), whole job, on synthetic
+          ccsdt_tilesize 40 -> 28 kernel tasks, 1.59e13 counted flops), the WHOLE job, on synthetic
           spin-orbital amplitudes/integrals of that shape (no converged amplitudes exist offline).
-  N > 1 : BASELINE.json configs[2] -- the caffeine cc-pVDZ shape (O=51, V=195, ccsdt_tilesize 28),
-          the first 96*N kernel tasks of its canonical task list, split over the N ranks by the
-          library's static cost-balanced partition (weak scaling: work per GPU is fixed); the only
+  N > 1 : BASELINE.json configs[4] at the north_star target size -- the synthetic (nocc, nvir) = (60, 500)
+          problem at ccsdt_tilesize 32 (16 320 kernel tasks, 1.24e17 counted flops in all): a strided sample
+          of TASKS_PER_GPU*N kernel tasks of its canonical list (every (n_tasks/sample)-th task, so the
+          sample has the job's mix of tile shapes and spin cases), handed out dynamically across the N
+          ranks through a process-shared counter (weak scaling: work per GPU is fixed); the only
           collective is one NCCL all-reduce of the two energies at the end of the step.
 `value`  = counted flops (the reference's own total_num_ops formula) / step time, tensors resident
            in HBM (N=1) or generated on the device (N>1) before the timed region.
 `e2e`    = the same metric through CCSD_T_Fused_Driver.execute-style use of the C ABI with HOST
            tensors: H2D of all five tensors from pinned memory inside the timed region and the
-           energies read back.
+           energies read back (N=1; at N>1 the 360 GB v2iabc of the workload cannot be host resident).
 """
 from __future__ import annotations
 
@@ -36,9 +38,15 @@ sys.path.insert(0, ROOT)
 METRIC = "(T) FP64 TFLOP/s (counted flops / (T) wall time)"
 SEED = 1234
 BENZENE = dict(name="benzene cc-pVDZ shape (BASELINE configs[1])", noa=21, nob=21, nva=93, nvb=93, ts=40)
-CAFFEINE = dict(name="caffeine cc-pVDZ shape (BASELINE configs[2])", noa=51, nob=51, nva=195, nvb=195, ts=28)
-TASKS_PER_GPU = 96
+SYNTH = dict(name="synthetic (nocc,nvir)=(60,500) (BASELINE configs[4], north_star target size)",
+             noa=60, nob=60, nva=500, nvb=500, ts=32)
+TASKS_PER_GPU = 24
 CPU_SAMPLE_TS = 14
+CPU_SAMPLE_TASKS = 3
+# dram__bytes_read.sum + dram__bytes_write.sum of one fused-kernel launch (ncu --set full, profiles/): the
+# N=1 workload's largest task, and the N>1 workload's task 5000
+NCU_TRAFFIC = {"benzene": {"bytes": 4.56e9, "task": "task 0 (21,21,21,40,40,40)", "report": "profiles/ncu_r01_benzene_task0.txt"},
+               "synth": {"bytes": 1.065e11, "task": "task 5000 (32,28,28,32,32,20)", "report": "profiles/ncu_r01_n60v500_task5000.txt"}}
 
 
 def orbital_energies(w):
@@ -99,9 +107,10 @@ def task_flops(orc, osp, restricted, task):
     return f
 
 
-def cpu_reference_sample(w, ntasks=1, ts=CPU_SAMPLE_TS):
+def cpu_reference_sample(w, ntasks=CPU_SAMPLE_TASKS, ts=CPU_SAMPLE_TS):
     """Times the reference's own CPU path (oracle/_ref, else the oracle port) on the first `ntasks`
-    kernel tasks of workload `w` re-tiled at tile size `ts` (bounded sample)."""
+    kernel tasks of workload `w` re-tiled at tile size `ts` (bounded sample: the CPU kernel needs two
+    T^6 buffers per task and ~2e10 flop/s on all cores, so full-size tiles are out of reach)."""
     from oracle.oracle import Oracle
     orc = Oracle()
     osp = orc.tiles(w["noa"], w["nob"], w["nva"], w["nvb"], ts)
@@ -125,11 +134,12 @@ def cpu_reference_sample(w, ntasks=1, ts=CPU_SAMPLE_TS):
         dt = time.perf_counter() - t0
     return {"value": flops / dt / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": kind, "seconds": dt,
             "sample": f"first {ntasks} kernel task(s) of the {w['name']} re-tiled at ccsdt_tilesize {ts} "
-                      f"({flops:.3e} counted flops), reference CPU kernel with OpenMP on {cores} threads"}
+                      f"({flops:.3e} counted flops), the reference's CPU (T) kernel (total_fused_ccsd_t_cpu, OpenMP) "
+                      f"on {cores} threads"}
 
 
 def run_reference_arm(args, rank):
-    w = BENZENE if args.gpus == 1 else CAFFEINE
+    w = BENZENE if args.gpus == 1 else SYNTH
     if rank != 0:
         return
     times, last = [], None
@@ -160,6 +170,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sub", default="", help="CTA box override, e.g. 1,1,2")
+    ap.add_argument("--workload", default="", choices=["", "benzene", "synth"], help="override the per-N default")
+    ap.add_argument("--static", action="store_true", help="N>1: static cost-balanced split instead of the shared counter")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -170,21 +182,27 @@ def main():
         run_reference_arm(args, rank)
         return
 
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
-    from exachem_b200 import _lib, driver as drv
+    from exachem_b200 import _lib, driver as drv, multigpu
 
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = _lib.load()
-    import ctypes as C
 
-    w = BENZENE if world == 1 else CAFFEINE
+    wl = args.workload or ("benzene" if world == 1 else "synth")
+    w = BENZENE if wl == "benzene" else SYNTH
     sp = drv.setup_mo_space(w["noa"], w["nob"], w["nva"], w["nvb"], w["ts"])
     evl = orbital_energies(w)
     tasks, _, _ = drv.enumerate_tasks(sp, True)
-    n_tasks = len(tasks) if world == 1 else min(len(tasks), TASKS_PER_GPU * world)
+    if wl == "benzene":
+        task_ids = np.arange(len(tasks), dtype=np.int64)                     # the whole job
+    else:
+        n_sample = min(len(tasks), TASKS_PER_GPU * world)
+        task_ids = (np.arange(n_sample, dtype=np.int64) * len(tasks)) // n_sample   # strided sample
 
     opts = {"rank": rank, "nranks": world}
     if args.sub:
@@ -203,11 +221,11 @@ def main():
 
     host = None
     n_orb = np.array([w["noa"], w["nob"], w["nva"], w["nvb"]])
-    if world == 1:
+    if wl == "benzene" and world == 1:
         # host tensors in pinned memory (produced by the device generator, read back once)
-        dims = {drv.T1: (sp.k_range[sp.noab:].sum(), sp.k_range[:sp.noab].sum(), 1, 1)}
-        O, V = int(dims[drv.T1][1]), int(dims[drv.T1][0])
-        dims.update({drv.T2: (V, V, O, O), drv.V_IJAB: (O, O, V, V), drv.V_IJKA: (O, O, O, V), drv.V_IABC: (O, V, V, V)})
+        O, V = int(sp.k_range[:sp.noab].sum()), int(sp.k_range[sp.noab:].sum())
+        dims = {drv.T1: (V, O, 1, 1), drv.T2: (V, V, O, O), drv.V_IJAB: (O, O, V, V), drv.V_IJKA: (O, O, O, V),
+                drv.V_IABC: (O, V, V, V)}
         host = {}
         for tid, d in dims.items():
             n = int(np.prod(d))
@@ -223,6 +241,16 @@ def main():
     else:
         ctx.set_synthetic(SEED)
 
+    counter = None
+    if world > 1 and not args.static:
+        name = f"ccsdt_b200_{os.environ.get('MASTER_PORT', '0')}"
+        if rank == 0:
+            counter = multigpu.SharedTaskCounter(name, create=True)
+        dist.barrier()
+        if rank != 0:
+            counter = multigpu.SharedTaskCounter(name, create=False)
+        ctx.set_task_counter(counter.address)
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -230,23 +258,27 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident():
-        e1, e2, st, _ = ctx.run(0, n_tasks)
-        if world > 1:
-            t = torch.tensor([e1, e2], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t)            # the one collective: E[T], E(T)
-            e1, e2 = t.tolist()
+        if counter is not None:
+            dist.barrier()
+            if rank == 0:
+                counter.reset()
+            dist.barrier()
+        e1, e2, st, _ = ctx.run_tasks(task_ids)
+        e1, e2 = multigpu.combine_energies(e1, e2, device="cuda")   # the one collective: E[T], E(T)
         return e1, e2, st
 
     def step_e2e():
         for tid, buf in host.items():
             ctx.put_dense(tid, buf)       # H2D from pinned host memory, inside the timed region
-        return ctx.run(0, n_tasks)[:3]
+        return ctx.run_tasks(task_ids)[:3]
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
         barrier()
         t0 = time.perf_counter()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
         agg = {"seconds_kernel": 0.0, "seconds_staging": 0.0, "counted_flops": 0.0, "kernel_launches": 0,
                "h2d_bytes": 0, "d2h_bytes": 0, "tasks_run": 0}
         e = None
@@ -255,17 +287,19 @@ def main():
             e = (e1, e2)
             for k in agg:
                 agg[k] += st[k]
+        ev1.record()
         barrier()
         dt = time.perf_counter() - t0
+        agg["device_ms"] = ev0.elapsed_time(ev1)
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-            f = torch.tensor([agg["counted_flops"], agg["kernel_launches"]], dtype=torch.float64, device="cuda")
+            f = torch.tensor([agg["counted_flops"], agg["kernel_launches"], agg["tasks_run"]], dtype=torch.float64, device="cuda")
             dist.all_reduce(f)
-            agg["flops_all"], agg["launches_all"] = float(f[0].item()), int(f[1].item())
+            agg["flops_all"], agg["launches_all"], agg["tasks_all"] = float(f[0].item()), int(f[1].item()), int(f[2].item())
         else:
-            agg["flops_all"], agg["launches_all"] = agg["counted_flops"], agg["kernel_launches"]
+            agg["flops_all"], agg["launches_all"], agg["tasks_all"] = agg["counted_flops"], agg["kernel_launches"], agg["tasks_run"]
         return dt, agg, e
 
     sampler = ClockSampler(local)
@@ -274,41 +308,50 @@ def main():
     dt, agg, energies = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
-    e2e = None
-    if world == 1:
-        dt2, agg2, _ = timed(step_e2e, max(1, min(args.steps, 3)), 1)
+    if host is not None:
         n2 = max(1, min(args.steps, 3))
+        dt2, agg2, _ = timed(step_e2e, n2, 1)
         e2e = {"value": agg2["flops_all"] / dt2 / 1e12, "unit": "TFLOP/s",
                "h2d_bytes_per_step": int(agg2["h2d_bytes"] / n2) + int(sum(b.nbytes for b in host.values())),
-               "d2h_bytes_per_step": int(agg2["d2h_bytes"] / n2), "ms_per_step": dt2 / n2 * 1e3}
+               "d2h_bytes_per_step": int(agg2["d2h_bytes"] / n2), "ms_per_step": dt2 / n2 * 1e3,
+               "api": "Context.put_dense x5 (pinned host tensors) + Context.run_tasks, i.e. what "
+                      "CCSD_T_Fused_Driver.execute does with dense host tensors"}
     else:
-        # at N > 1 the tensors are generated on the device; the end-to-end number is quoted at N = 1
         e2e = {"value": agg["flops_all"] / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": 0,
                "d2h_bytes_per_step": int(agg["d2h_bytes"] / args.steps),
-               "note": "device-generated tensors; host-tensor e2e is measured at N=1"}
+               "note": "tensors are generated on the device (v2iabc of this workload is 360 GB and cannot be "
+                       "host resident); the host-tensor end-to-end number is measured at N=1"}
 
     if rank == 0:
         value = agg["flops_all"] / dt / 1e12
-        peak = max(peaks.values())
+        peak = peaks["dmma"]
         kernel_tf = agg["counted_flops"] / max(agg["seconds_kernel"], 1e-12) / 1e12
+        traffic = NCU_TRAFFIC[wl]
         line = {
             "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "nocc": w["noa"], "nvir": w["nva"], "ccsdt_tilesize": w["ts"],
-                       "kernel_tasks_per_step": int(n_tasks), "parallelism": f"task-parallel x{world}",
-                       "l2_policy": "operand panels of one task (>= 0.4 GB) exceed the 126 MB L2",
-                       "cta_box": args.sub or "default"},
+                       "kernel_tasks_per_step": int(len(task_ids)),
+                       "task_selection": "whole job" if wl == "benzene" else
+                       f"strided sample: every {len(tasks) // len(task_ids)}-th of {len(tasks)} kernel tasks",
+                       "parallelism": f"task-parallel x{world}" + ("" if world == 1 else
+                                                                   (", static LPT split" if args.static else ", shared-counter dynamic hand-out")),
+                       "l2_policy": "inputs larger than L2: the operand panels of one task (0.4-2.7 GB) exceed the 126 MB L2 "
+                                    "and are rebuilt per task",
+                       "cta_box": args.sub or "default (2,2,2,8,8,8), 3 CTAs/SM"},
             "t_wall_s_per_step": dt / args.steps,
+            "fraction_of_fp64_peak": value / (world * peak),
             "energies": {"E[T]": energies[0], "E(T)": energies[1]},
             "roofline": {"bound": "tensor", "achieved": kernel_tf, "peak": peak, "unit": "TFLOP/s",
-                         "frac": kernel_tf / peak, "traffic": None,
-                         "kernel": "fused_t_dmma_kernel (FP64 DMMA m8n8k4)",
-                         "peak_source": "measured in this run by ccsdt_probe_fp64_peak: register-resident "
-                                        "DMMA.8x8x4 / DFMA issue loops (MEASURED_PEAKS.json has no FP64 entry)",
+                         "frac": kernel_tf / peak, "traffic": traffic["bytes"],
+                         "traffic_note": f"DRAM read+write bytes of ONE fused-kernel launch ({traffic['task']}) from {traffic['report']}",
+                         "kernel": "fused_t_dmma_kernel (FP64 DMMA m8n8k4, sm_100a)",
+                         "peak_source": "measured in this run by ccsdt_probe_fp64_peak: register-resident DMMA.8x8x4 issue loop "
+                                        "(MEASURED_PEAKS.json has no FP64 entry; nominal HGX B200 FP64 = 37 TFLOP/s)",
                          "peaks_measured": peaks,
-                         "achieved_def": "reference-counted flops of the tasks / CUDA-event time of the fused "
-                                         "kernel launches on their stream"},
+                         "achieved_def": "reference-counted flops of this rank's tasks / CUDA-event time of its fused-kernel "
+                                         "launches on their stream (rank 0)"},
             "e2e": e2e, "gpu_launches": int(agg["launches_all"]), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -320,6 +363,9 @@ def main():
                 line["cpu_baseline"] = {"value": None, "error": repr(ex)}
         print(json.dumps(line), flush=True)
     ctx.close()
+    if counter is not None:
+        dist.barrier()
+        counter.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -49,6 +49,7 @@ SIGNATURES = {
     "ccsdt_set_synthetic": (C.c_int, [C.c_void_p, C.c_uint64]),
     "ccsdt_set_task_counter": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ccsdt_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _dp, C.POINTER(Stats)]),
+    "ccsdt_run_tasks": (C.c_int, [C.c_void_p, _i64p, C.c_int64, _dp, _dp, C.POINTER(Stats)]),
     "ccsdt_probe_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp]),
     "ccsdt_probe_mainloop": (C.c_int, [C.c_int] * 6 + [_dp]),
     "ccsdt_probe_dmma_layout": (C.c_int, [C.c_int, _dp, _dp, _dp]),

@@ -77,6 +77,7 @@ struct ccsdt_ctx {
   int64_t              n_outer = 0;
 
   double*                        dense[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t                         dense_elems[5] = {0, 0, 0, 0, 0};
   std::map<BlockKey, BlockEntry> blocks;
   size_t                         block_bytes = 0, block_budget = 0;
   int64_t                        use_clock = 0;
@@ -731,6 +732,109 @@ int collect_timing(ccsdt_ctx* ctx, StageBuf& b) {
 
 } // namespace
 
+static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool use_global_split, double energies[2],
+                         double* per_task, ccsdt_stats* stats_out) {
+  cudaSetDevice(ctx->device);
+  const auto t0 = std::chrono::high_resolution_clock::now();
+  ctx->stats    = ccsdt_stats{};
+  energies[0] = energies[1] = 0.0;
+  const int64_t nids = (int64_t) ids.size();
+
+  // Task hand-out.  Static: the tasks the cost-balanced split gave this rank, in canonical order.
+  // Dynamic (a process-shared counter was set): every rank walks the SAME list, the tasks of the range in
+  // descending cost order, and claims the next unclaimed entry with one atomic fetch-add -- the role of
+  // the reference's AtomicCounterGA (ccsd_t_fused_driver.hpp:169-172, 456), with longest-task-first order.
+  std::vector<int64_t> mine, order;
+  std::vector<int64_t> pos_of(ctx->tasks.size(), -1); // position in ids (for per_task)
+  for(int64_t k = 0; k < nids; k++) pos_of[ids[k]] = k;
+  if(ctx->task_counter) {
+    order = ids;
+    std::vector<long double> cost(ctx->tasks.size(), 0);
+    for(int64_t id: ids) cost[id] = task_ops(ctx->sp, ctx->tasks[id]);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cost[a] > cost[b]; });
+  }
+  else if(use_global_split || ctx->opt.nranks <= 1) {
+    for(int64_t id: ids)
+      if(ctx->owner.empty() || ctx->owner[id] == ctx->opt.rank) order.push_back(id);
+  }
+  else {
+    // static split of this list alone: longest-processing-time greedy, identical on every rank
+    std::vector<Task> sub;
+    for(int64_t id: ids) sub.push_back(ctx->tasks[id]);
+    const std::vector<int32_t> own = partition_tasks(ctx->sp, sub, ctx->opt.nranks);
+    for(int64_t k = 0; k < nids; k++)
+      if(own[k] == ctx->opt.rank) order.push_back(ids[k]);
+  }
+  int64_t cursor = 0;
+  auto    next_task = [&]() -> int64_t {
+    const int64_t k = ctx->task_counter ? __atomic_fetch_add(ctx->task_counter, (int64_t) 1, __ATOMIC_RELAXED) : cursor++;
+    return k < (int64_t) order.size() ? order[k] : -1;
+  };
+  if(per_task) std::fill(per_task, per_task + 2 * nids, 0.0);
+
+  if(!order.empty()) {
+    if(int rc = ensure_pools(ctx)) return rc;
+    const int64_t cap = (int64_t) order.size();
+    if(cap > ctx->task_energy_cap) {
+      if(ctx->d_task_energy) CK(cudaFree(ctx->d_task_energy));
+      ctx->task_energy_cap = cap + 16;
+      CK(cudaMalloc(&ctx->d_task_energy, (size_t) ctx->task_energy_cap * 16));
+    }
+    CK(cudaMemsetAsync(ctx->d_error, 0, 4, ctx->s_compute));
+    const int nbuf = ctx->opt.overlap ? 2 : 1;
+    for(int64_t j = 0;; j++) {
+      const int64_t ti = next_task();
+      if(ti < 0) break;
+      mine.push_back(ti);
+      StageBuf& b = ctx->buf[j % nbuf];
+      // the buffer's previous task must have finished computing before its panels are rebuilt
+      if(b.timing_pending) {
+        if(int rc = collect_timing(ctx, b)) return rc;
+      }
+      CK(cudaStreamWaitEvent(ctx->s_stage, b.done, 0));
+      if(int rc = stage_task(ctx, b, ctx->tasks[ti])) return rc;
+      if(int rc = launch_task(ctx, b, j)) return rc;
+      ctx->stats.counted_flops += (double) task_ops(ctx->sp, ctx->tasks[ti]);
+    }
+    const int64_t n = (int64_t) mine.size();
+    for(int i = 0; i < nbuf; i++)
+      if(int rc = collect_timing(ctx, ctx->buf[i])) return rc;
+    cudaError_t e = cudaStreamSynchronize(ctx->s_compute);
+    if(e != cudaSuccess) {
+      return ctx->fail(std::string("fused kernel failed: ") + cudaGetErrorName(e) + " " + cudaGetErrorString(e) +
+                       " (a pipeline timeout traps instead of hanging)", 9);
+    }
+    CK(cudaStreamSynchronize(ctx->s_stage));
+    uint32_t flag = 0;
+    CK(cudaMemcpy(&flag, ctx->d_error, 4, cudaMemcpyDeviceToHost));
+    if(flag) return ctx->fail("device error flag " + std::to_string(flag), 9);
+    std::vector<double> e_host((size_t) 2 * std::max<int64_t>(n, 1));
+    if(n) CK(cudaMemcpy(e_host.data(), ctx->d_task_energy, (size_t) n * 16, cudaMemcpyDeviceToHost));
+    ctx->stats.d2h_bytes += n * 16;
+    // reduction order: boxes in box-id order inside a task (fixed tree), then this rank's tasks in
+    // canonical task order (whatever order they were claimed in)
+    std::vector<int64_t> slot_of(n);
+    for(int64_t j = 0; j < n; j++) slot_of[j] = j;
+    std::sort(slot_of.begin(), slot_of.end(), [&](int64_t a, int64_t b) { return mine[a] < mine[b]; });
+    for(int64_t jj = 0; jj < n; jj++) {
+      const int64_t j  = slot_of[jj];
+      const double  f  = ctx->tasks[mine[j]].factor;
+      const double  e1 = f * e_host[2 * j], e2 = f * e_host[2 * j + 1];
+      energies[0] += e1;
+      energies[1] += e2;
+      if(per_task) {
+        per_task[2 * pos_of[mine[j]]]     = e1;
+        per_task[2 * pos_of[mine[j]] + 1] = e2;
+      }
+    }
+    ctx->stats.tasks_run = n;
+  }
+  const auto t1            = std::chrono::high_resolution_clock::now();
+  ctx->stats.seconds_total = std::chrono::duration<double>(t1 - t0).count();
+  if(stats_out) *stats_out = ctx->stats;
+  return 0;
+}
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -927,9 +1031,19 @@ int ccsdt_put_dense(ccsdt_ctx* ctx, int tensor, const double* host) {
   cudaSetDevice(ctx->device);
   size_t n = 1;
   for(const char* k = kKinds[tensor]; *k; k++) n *= (size_t) dim_full(ctx->sp, *k);
-  if(ctx->dense[tensor]) cudaFree(ctx->dense[tensor]);
-  CK(cudaMalloc(&ctx->dense[tensor], n * 8));
-  CK(cudaMemcpy(ctx->dense[tensor], host, n * 8, cudaMemcpyHostToDevice));
+  // re-uploads (same space) reuse the allocation; the copy is stream-ordered before the next panel build
+  if(ctx->dense[tensor] && ctx->dense_elems[tensor] != n) {
+    CK(cudaStreamSynchronize(ctx->s_compute));
+    CK(cudaFree(ctx->dense[tensor]));
+    ctx->dense[tensor] = nullptr;
+  }
+  if(!ctx->dense[tensor]) {
+    CK(cudaMalloc(&ctx->dense[tensor], n * 8));
+    ctx->dense_elems[tensor] = n;
+  }
+  CK(cudaStreamSynchronize(ctx->s_compute)); // a running task may still read the old contents
+  CK(cudaMemcpyAsync(ctx->dense[tensor], host, n * 8, cudaMemcpyHostToDevice, ctx->s_stage));
+  CK(cudaStreamSynchronize(ctx->s_stage));   // the caller may reuse `host` on return
   ctx->stats.h2d_bytes += (int64_t) n * 8;
   ctx->synthetic = false;
   return 0;
@@ -985,102 +1099,24 @@ int ccsdt_run(ccsdt_ctx* ctx, int64_t task_begin, int64_t task_end, double energ
               ccsdt_stats* stats_out) {
   if(!ctx || !energies) return 1;
   if(!ctx->have_space) return ctx->fail("ccsdt_set_space must be called first");
-  cudaSetDevice(ctx->device);
-  const auto    t0 = std::chrono::high_resolution_clock::now();
   const int64_t nt = (int64_t) ctx->tasks.size();
   if(task_end < 0 || task_end > nt) task_end = nt;
   if(task_begin < 0) task_begin = 0;
   if(task_begin > task_end) task_begin = task_end;
-  const int64_t h2d0 = ctx->stats.h2d_bytes;
-  const int64_t fetched0 = ctx->stats.blocks_fetched;
-  ctx->stats     = ccsdt_stats{};
-  ctx->stats.h2d_bytes = 0;
-  (void) h2d0; (void) fetched0;
-  energies[0] = energies[1] = 0.0;
+  std::vector<int64_t> ids;
+  for(int64_t i = task_begin; i < task_end; i++) ids.push_back(i);
+  // the whole list uses the split computed at set_space/set_options; a sub-range re-balances itself
+  return run_task_list(ctx, ids, task_begin == 0 && task_end == nt, energies, per_task, stats_out);
+}
 
-  // Task hand-out.  Static: the tasks the cost-balanced split gave this rank, in canonical order.
-  // Dynamic (a process-shared counter was set): every rank walks the SAME list, the tasks of the range in
-  // descending cost order, and claims the next unclaimed entry with one atomic fetch-add -- the role of
-  // the reference's AtomicCounterGA (ccsd_t_fused_driver.hpp:169-172, 456), with longest-task-first order.
-  std::vector<int64_t> mine, order;
-  if(ctx->task_counter) {
-    for(int64_t i = task_begin; i < task_end; i++) order.push_back(i);
-    std::vector<long double> cost(ctx->tasks.size());
-    for(int64_t i = task_begin; i < task_end; i++) cost[i] = task_ops(ctx->sp, ctx->tasks[i]);
-    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cost[a] > cost[b]; });
-  }
-  else {
-    for(int64_t i = task_begin; i < task_end; i++)
-      if(ctx->owner.empty() || ctx->owner[i] == ctx->opt.rank) order.push_back(i);
-  }
-  int64_t cursor = 0;
-  auto    next_task = [&]() -> int64_t {
-    const int64_t k = ctx->task_counter ? __atomic_fetch_add(ctx->task_counter, (int64_t) 1, __ATOMIC_RELAXED) : cursor++;
-    return k < (int64_t) order.size() ? order[k] : -1;
-  };
-  if(per_task) std::fill(per_task, per_task + 2 * (task_end - task_begin), 0.0);
-
-  if(!order.empty()) {
-    if(int rc = ensure_pools(ctx)) return rc;
-    const int64_t cap = (int64_t) order.size();
-    if(cap > ctx->task_energy_cap) {
-      if(ctx->d_task_energy) CK(cudaFree(ctx->d_task_energy));
-      ctx->task_energy_cap = cap + 16;
-      CK(cudaMalloc(&ctx->d_task_energy, (size_t) ctx->task_energy_cap * 16));
-    }
-    CK(cudaMemsetAsync(ctx->d_error, 0, 4, ctx->s_compute));
-    const int nbuf = ctx->opt.overlap ? 2 : 1;
-    for(int64_t j = 0;; j++) {
-      const int64_t ti = next_task();
-      if(ti < 0) break;
-      mine.push_back(ti);
-      StageBuf& b = ctx->buf[j % nbuf];
-      // the buffer's previous task must have finished computing before its panels are rebuilt
-      if(b.timing_pending) {
-        if(int rc = collect_timing(ctx, b)) return rc;
-      }
-      CK(cudaStreamWaitEvent(ctx->s_stage, b.done, 0));
-      if(int rc = stage_task(ctx, b, ctx->tasks[ti])) return rc;
-      if(int rc = launch_task(ctx, b, j)) return rc;
-      ctx->stats.counted_flops += (double) task_ops(ctx->sp, ctx->tasks[ti]);
-    }
-    const int64_t n = (int64_t) mine.size();
-    for(int i = 0; i < nbuf; i++)
-      if(int rc = collect_timing(ctx, ctx->buf[i])) return rc;
-    cudaError_t e = cudaStreamSynchronize(ctx->s_compute);
-    if(e != cudaSuccess) {
-      return ctx->fail(std::string("fused kernel failed: ") + cudaGetErrorName(e) + " " + cudaGetErrorString(e) +
-                       " (a pipeline timeout traps instead of hanging)", 9);
-    }
-    CK(cudaStreamSynchronize(ctx->s_stage));
-    uint32_t flag = 0;
-    CK(cudaMemcpy(&flag, ctx->d_error, 4, cudaMemcpyDeviceToHost));
-    if(flag) return ctx->fail("device error flag " + std::to_string(flag), 9);
-    std::vector<double> e_host((size_t) 2 * std::max<int64_t>(n, 1));
-    if(n) CK(cudaMemcpy(e_host.data(), ctx->d_task_energy, (size_t) n * 16, cudaMemcpyDeviceToHost));
-    ctx->stats.d2h_bytes += n * 16;
-    // reduction order: boxes in box-id order inside a task (fixed tree), then this rank's tasks in
-    // canonical task order (whatever order they were claimed in)
-    std::vector<int64_t> slot_of(n);
-    for(int64_t j = 0; j < n; j++) slot_of[j] = j;
-    std::sort(slot_of.begin(), slot_of.end(), [&](int64_t a, int64_t b) { return mine[a] < mine[b]; });
-    for(int64_t jj = 0; jj < n; jj++) {
-      const int64_t j  = slot_of[jj];
-      const double  f  = ctx->tasks[mine[j]].factor;
-      const double  e1 = f * e_host[2 * j], e2 = f * e_host[2 * j + 1];
-      energies[0] += e1;
-      energies[1] += e2;
-      if(per_task) {
-        per_task[2 * (mine[j] - task_begin)]     = e1;
-        per_task[2 * (mine[j] - task_begin) + 1] = e2;
-      }
-    }
-    ctx->stats.tasks_run = n;
-  }
-  const auto t1            = std::chrono::high_resolution_clock::now();
-  ctx->stats.seconds_total = std::chrono::duration<double>(t1 - t0).count();
-  if(stats_out) *stats_out = ctx->stats;
-  return 0;
+int ccsdt_run_tasks(ccsdt_ctx* ctx, const int64_t* task_ids, int64_t n, double energies[2], double* per_task,
+                    ccsdt_stats* stats_out) {
+  if(!ctx || !energies || (n > 0 && !task_ids)) return 1;
+  if(!ctx->have_space) return ctx->fail("ccsdt_set_space must be called first");
+  std::vector<int64_t> ids(task_ids, task_ids + (n > 0 ? n : 0));
+  for(int64_t id: ids)
+    if(id < 0 || id >= (int64_t) ctx->tasks.size()) return ctx->fail("task id out of range");
+  return run_task_list(ctx, ids, false, energies, per_task, stats_out);
 }
 
 // ---- diagnostics --------------------------------------------------------------------------------

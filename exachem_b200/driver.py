@@ -218,6 +218,18 @@ class Context:
         return float(e[0]), float(e[1]), stats, pt
 
 
+    def run_tasks(self, task_ids, per_task=False):
+        """explicit list of task ids (indices into the canonical list)."""
+        ids = np.ascontiguousarray(task_ids, np.int64)
+        e = np.zeros(2)
+        st = Stats()
+        pt = np.zeros((len(ids), 2)) if per_task else None
+        self._ck(self.L.ccsdt_run_tasks(self.h, _p(ids, _lib._i64p), len(ids), _p(e, _lib._dp),
+                                        _p(pt, _lib._dp) if pt is not None else None, C.byref(st)))
+        stats = {k: getattr(st, k) for k, _ in Stats._fields_}
+        return float(e[0]), float(e[1]), stats, pt
+
+
 class _BlockSource:
     """Adapts 'dense ndarray' or 'object with .get(bid)' to the Context operand API."""
 

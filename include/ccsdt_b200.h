@@ -19,7 +19,7 @@
  *                           ccsd_t_all_fused_singles.hpp:200,304; ..._doubles1.hpp:222,237,282;
  *                           ..._doubles2.hpp:215,230,335  (and the six LRUCache arguments: the HBM block
  *                           store replaces them)
- *   ccsdt_run            <- execute's task loop + ccsd_t_fully_fused_none_df_none_task
+ *   ccsdt_run / ccsdt_run_tasks <- execute's task loop + ccsd_t_fully_fused_none_df_none_task
  *                           ccsd_t_all_fused.hpp:77-286 + the kernel launcher ccsd_t_all_fused_gpu.cu:2571
  *                           + hostEnergyReduce ccsd_t_all_fused.hpp:19-32; returns the rank-partial
  *                           (energy1 = E[T], energy2 = E(T)) the caller reduces at ccsd_t.cpp:262-263
@@ -137,6 +137,12 @@ CCSDT_API int ccsdt_set_task_counter(ccsdt_ctx* ctx, int64_t* counter);
  * per task of the range (zeros for tasks owned by other ranks). */
 CCSDT_API int ccsdt_run(ccsdt_ctx* ctx, int64_t task_begin, int64_t task_end, double energies[2],
               double* per_task, ccsdt_stats* stats);
+
+/* same for an explicit list of task ids (indices into the canonical list); per_task is indexed by list
+ * position.  With nranks > 1 and no task counter the list is split among the ranks on its own
+ * (longest-processing-time greedy, identical on every rank). */
+CCSDT_API int ccsdt_run_tasks(ccsdt_ctx* ctx, const int64_t* task_ids, int64_t n, double energies[2],
+                              double* per_task, ccsdt_stats* stats);
 
 /* diagnostics used by tests and bench (device microbenchmarks and unit probes) */
 CCSDT_API int ccsdt_probe_fp64_peak(int device, int use_dmma, int iters, double* tflops, double* ms);
