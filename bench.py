@@ -142,6 +142,8 @@ def run_reference_arm(args, rank):
     w = BENZENE if args.gpus == 1 else SYNTH
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the reference CPU kernel is OpenMP and gets every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     times, last = [], None
     for i in range(args.warmup + args.steps):
         last = cpu_reference_sample(w)

@@ -64,6 +64,11 @@ class SharedTaskCounter:
             self.shm = shared_memory.SharedMemory(name=name, create=True, size=64)
         else:
             self.shm = shared_memory.SharedMemory(name=name)
+            try:  # only the creator owns the segment: keep the attaching ranks out of the resource tracker
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:  # noqa: BLE001
+                pass
         self.owner = create
         self._c = ctypes.c_int64.from_buffer(self.shm.buf)
         self.address = ctypes.addressof(self._c)
