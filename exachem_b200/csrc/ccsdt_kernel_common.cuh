@@ -35,9 +35,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // bounded wait: a pipeline bug must end in a trap (reported as a CUDA error), never in a hung GPU.
 // The slow path is kept out of line: the wait is inlined at every pipeline step and the kernel's hot
 // code has to stay small (instruction cache).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(bar), "r"(parity), "r"(ns)
+               : "memory");
+  return ok != 0;
+}
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t* error_flag, int tag) {
+  // long suspend hint + back-off: a waiting warp (the producer, almost always) must not eat issue slots of
+  // the DMMA warps that share its scheduler
   const long long t0 = clock64();
-  while(!mbar_try_wait(bar, parity)) {
+  while(!mbar_try_wait_hint(bar, parity, 20000u)) {
+    __nanosleep(100);
     if(clock64() - t0 > 4000000000ll) { // ~2 s
       if(error_flag) atomicExch(error_flag, 0xDEAD0000u | (uint32_t) tag);
       __threadfence_system();

@@ -115,10 +115,18 @@ __device__ __forceinline__ double s1_term(const double (&tq)[32], const double* 
 #pragma unroll
     for(int q = 0; q < 4; q++)
       bv[o][q] = __ldg(pb + (o >> 1) * db[O1] + (o & 1) * db[O2] + (q >> 1) * db[1] + (q & 1) * db[0]);
+  // sum over (hole of a, particle bits q) of a * (sum over the other two holes of tq * b): 40 FP64 operations
   double sum = 0.0;
 #pragma unroll
-  for(int e = 0; e < 32; e++)
-    sum += tq[e] * (av[(e >> HB) & 1][e & 3] * bv[(((e >> O1) & 1) << 1) | ((e >> O2) & 1)][e & 3]);
+  for(int h = 0; h < 2; h++)
+#pragma unroll
+    for(int q = 0; q < 4; q++) {
+      double inner = 0.0;
+#pragma unroll
+      for(int o = 0; o < 4; o++)
+        inner = fma(tq[(h << HB) | ((o >> 1) << O1) | ((o & 1) << O2) | q], bv[o][q], inner);
+      sum = fma(av[h][q], inner, sum);
+    }
   return sum;
 }
 
@@ -272,8 +280,7 @@ __device__ __forceinline__ void consume_term(double (&acc)[32], const TaskParams
           fh[hx][ql] = lds_f64(jn + hpp_off[hx][ql]);
         }
     }
-    __syncwarp();
-    if(lane == 0) mbar_arrive(empty_bar + 8 * ring.stage);
+    mbar_arrive(empty_bar + 8 * ring.stage); // every lane arrives: no warp-wide reconvergence in the loop
     ring = nxt;
     base = next_base;
   }
@@ -356,7 +363,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
   if(tid == 0) {
     for(int s = 0; s < p.stages; s++) {
       mbar_init(full_bar + 8 * s, 1);
-      mbar_init(empty_bar + 8 * s, (uint32_t) ncw);
+      mbar_init(empty_bar + 8 * s, (uint32_t) (ncw * 32));
     }
     mbar_fence_init();
   }

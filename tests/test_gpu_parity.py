@@ -267,3 +267,61 @@ def test_dynamic_task_counter_two_claimants():
     pt = out[0][3] + out[1][3]
     assert np.array_equal(pt, tot[3])                      # each task computed once, bit-identical to the static run
     assert abs(out[0][0] + out[1][0] - tot[0]) < 1e-12 and abs(out[0][1] + out[1][1] - tot[1]) < 1e-12
+
+
+def test_full_width_tiles_vs_oracle(orc):
+    """ccsdt_tilesize 40 (ExaChem's default): five 8-wide particle boxes per index, whole job against the oracle"""
+    oa = ob = 6
+    va = vb = 40
+    sp, osp = drv.setup_mo_space(oa, ob, va, vb, 40), orc.tiles(oa, ob, va, vb, 40)
+    T = syn.dense_all(syn.Orbitals(oa, ob, va, vb), 40)
+    ref = orc.run(osp, T, True, per_task=True)
+    e1, e2, st, pt = run_gpu(sp, T, True)
+    assert _close(e1, ref[0]) and _close(e2, ref[1])
+    assert np.allclose(pt, ref[2], rtol=1e-11, atol=ATOL)
+    assert st["counted_flops"] == orc.count_ops(osp, True)
+
+
+def test_headline_size_task_is_box_shape_independent():
+    """BASELINE full size, (nocc, nvir) = (60, 500) at ccsdt_tilesize 32 on device-generated tensors: one
+    32^6 task (1.08e13 counted flops, 262 144 CTA boxes) must give the same energies for every CTA box
+    shape / ring depth (different boxes, bricks and partial sums; same elements), and a ragged task must too."""
+    no, nv, ts = 60, 500, 32
+    sp = drv.setup_mo_space(no, no, nv, nv, ts)
+    evl = syn.Orbitals(no, no, nv, nv).orbital_energies()
+    tasks, _, _ = drv.enumerate_tasks(sp, True)
+    ragged = next(i for i, t in enumerate(tasks) if sp.k_range[t[5]] == 20 and sp.k_range[t[0]] == 32 and sp.k_range[t[2]] == 28)
+    res = {}
+    for name, opts in (("default", {}), ("box_1_1_2", dict(sub=(1, 1, 2))), ("two_stage", dict(stages=2, ctas_per_sm=2))):
+        ctx = drv.Context(0)
+        try:
+            ctx.set_options(**opts)
+            ctx.set_space(sp, evl, True)
+            ctx.set_synthetic(1234)
+            res[name] = ctx.run_tasks([0, ragged], per_task=True)
+        finally:
+            ctx.close()
+    ref = res["default"]
+    assert ref[2]["tasks_run"] == 2 and ref[2]["counted_flops"] > 1.0e13
+    assert np.all(np.isfinite(ref[3])) and np.all(ref[3] < 0)          # D < 0 everywhere: E[T] contributions are negative
+    for name in ("box_1_1_2", "two_stage"):
+        assert np.allclose(res[name][3], ref[3], rtol=1e-11, atol=0), name
+
+
+def test_task_list_subset_and_order_independent():
+    """ccsdt_run_tasks: per-task energies do not depend on which other tasks run or in what order"""
+    sp = drv.setup_mo_space(6, 6, 17, 17, 5)
+    T = syn.dense_all(syn.Orbitals(6, 6, 17, 17), 2)
+    full = run_gpu(sp, T, True)
+    n = len(drv.enumerate_tasks(sp, True)[0])
+    ids = np.random.default_rng(0).permutation(n)[: n // 3]
+    ctx = drv.Context(0)
+    try:
+        ctx.set_space(sp, T["evl"], True)
+        for tid, k in ((drv.T1, "t1"), (drv.T2, "t2"), (drv.V_IJAB, "v2ijab"), (drv.V_IJKA, "v2ijka"), (drv.V_IABC, "v2iabc")):
+            ctx.put_dense(tid, T[k])
+        e1, e2, st, pt = ctx.run_tasks(ids, per_task=True)
+    finally:
+        ctx.close()
+    assert np.array_equal(pt, full[3][ids]) and st["tasks_run"] == len(ids)
+    assert abs(e1 - full[3][ids, 0].sum()) < 1e-12
