@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libccsdt_b200.so")
+SO_PATH = os.environ.get("CCSDT_B200_LIB") or os.path.join(HERE, "libccsdt_b200.so")  # override: A/B builds in tools/
 
 _dp = C.POINTER(C.c_double)
 _i64p = C.POINTER(C.c_int64)

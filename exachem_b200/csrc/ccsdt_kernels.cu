@@ -233,8 +233,8 @@ __device__ __forceinline__ void consume_term(double (&acc)[32], const TaskParams
   // One 4-wide k-step = 16 DMMAs from 4 HPP fragments (fh) and 4 HHP fragments (fg), all single-buffered:
   // the DMMAs run fh-major, each fh is re-requested for the next step right after its fourth and last use,
   // each fg after its last use in the final group -- every reload sits at least three DMMA issue slots
-  // (~48 cycles) ahead of its first use, which covers the shared-memory latency.  The k-loop is NOT
-  // unrolled: the six (HH, A_HPP) instantiations of this loop are the whole hot code of the kernel and must
+  // (~48 cycles) ahead of its first use, which covers the shared-memory latency.  The k-loop is unrolled by
+  // two only (measured: x2 +1.3 %, x4 +2 % on long K but -2 % on short K): the six (HH, A_HPP) instantiations of this loop are the whole hot code of the kernel and must
   // stay resident in the instruction cache while co-resident CTAs run different terms.
   // Loads past the end of the term read valid but unused shared memory (no conditional loads).
   double fh[2][2], fg[2][2];
@@ -254,7 +254,7 @@ __device__ __forceinline__ void consume_term(double (&acc)[32], const TaskParams
     Ring           nxt  = ring;
     nxt.advance((uint32_t) p.stages);
     const uint32_t next_base = last ? base : ring_base + nxt.stage * (uint32_t) p.stage_bytes;
-#pragma unroll 1
+#pragma unroll 2
     for(uint32_t j = 0; j < nj; j++) {
       uint32_t jn; // shared-memory address (without fragment offset) of the next step's fragments
       if(j == 3) {
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(512) mainloop_probe_kernel(double* out, int it
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   double*        sm   = reinterpret_cast<double*>(smem_raw + (base - smem_u32(smem_raw)));
-  for(int i = threadIdx.x; i < 64 * 16 * 4; i += blockDim.x) sm[i] = 1e-3 * (i % 7);
+  for(int i = threadIdx.x; i < 41 * 1024 / 8; i += blockDim.x) sm[i] = 1e-3 * (i % 7);
   __syncthreads();
   const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int      q = lane >> 2, l3 = lane & 3;
@@ -727,11 +727,11 @@ __global__ void __launch_bounds__(512) mainloop_probe_kernel(double* out, int it
 #pragma unroll
   for(int i = 0; i < TA; i++) offa[i] = (uint32_t) (((warp * 3 + i) & 31) * 8 * ROW_BYTES) + lane_const;
 #pragma unroll
-  for(int i = 0; i < TB; i++) offb[i] = (uint32_t) (((warp * 5 + i + 32) & 63) * 8 * ROW_BYTES) + lane_const;
+  for(int i = 0; i < TB; i++) offb[i] = (uint32_t) (((warp * 5 + i + 16) & 31) * 8 * ROW_BYTES) + lane_const;
   for(int it = 0; it < iters; it++) {
 #pragma unroll
     for(uint32_t j = 0; j < 4; j++) {
-      const uint32_t jo = base + ((j ^ jx) << 5) + (uint32_t) ((it & 3) * 64 * ROW_BYTES);
+      const uint32_t jo = base + ((j ^ jx) << 5) + (uint32_t) ((it & 1) * 64 * ROW_BYTES);
       double         fa[TA], fb[TB];
 #pragma unroll
       for(int i = 0; i < TA; i++) fa[i] = lds_f64(jo + offa[i]);
@@ -749,26 +749,106 @@ __global__ void __launch_bounds__(512) mainloop_probe_kernel(double* out, int it
   out[(int64_t) blockIdx.x * blockDim.x + threadIdx.x] = sacc;
 }
 
+// MODE 1: the product kernel's k-step loop shape (rolled, 16 DMMAs per trip, fragments reloaded right after
+// their last use) without any barrier; MODE 2: plus the per-slab mbarrier traffic (every lane arrives on an
+// "empty" barrier, try_wait on a completed "full" one).  ta/tb select MODE here: (1,0) and (2,0).
+template<int MODE>
+__global__ void __launch_bounds__(128) mainloop_probe2_kernel(double* out, int iters) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  double*        sm   = reinterpret_cast<double*>(smem_raw + (base - smem_u32(smem_raw)));
+  for(int i = threadIdx.x; i < 41 * 1024 / 8; i += blockDim.x) sm[i] = 1e-3 * (i % 7);
+  if(threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), blockDim.x);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if(threadIdx.x == 0) mbar_arrive(smem_u32(&bars[0])); // phase 0 of the "full" barrier is complete for good
+  __syncthreads();
+  const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int      q = frag_row(lane >> 2), l3 = lane & 3;
+  const uint32_t lane_const = (uint32_t) (q * ROW_BYTES + ((((l3 >> 1) ^ (q & 1)) << 4) | ((l3 & 1) << 3)));
+  const uint32_t jx = (uint32_t) (q >> 1);
+  double         acc[32];
+#pragma unroll
+  for(int i = 0; i < 32; i++) acc[i] = 0.0;
+  uint32_t hpp_off[2][2], hhp_off[2][2];
+#pragma unroll
+  for(int x = 0; x < 2; x++)
+#pragma unroll
+    for(int y = 0; y < 2; y++) {
+      hpp_off[x][y] = (uint32_t) (((warp * 3 + 2 * x + y) & 31) * 8 * ROW_BYTES) + lane_const;
+      hhp_off[x][y] = (uint32_t) (((warp * 5 + 2 * x + y + 16) & 31) * 8 * ROW_BYTES) + lane_const;
+    }
+  double fh[2][2], fg[2][2];
+#pragma unroll
+  for(int x = 0; x < 2; x++)
+#pragma unroll
+    for(int y = 0; y < 2; y++) {
+      fh[x][y] = lds_f64(base + (jx << 5) + hpp_off[x][y]);
+      fg[x][y] = lds_f64(base + (jx << 5) + hhp_off[x][y]);
+    }
+  uint32_t phase = 0;
+  for(int s = 0; s < iters; s++) {
+#pragma unroll(MODE == 3 ? 2 : (MODE == 4 ? 4 : 1))
+    for(uint32_t j = 0; j < 4; j++) {
+      uint32_t jn;
+      if(j == 3) {
+        if(MODE == 2) mbar_wait(smem_u32(&bars[0]), 0, nullptr, 9);
+        jn = base + (jx << 5) + (uint32_t) (((s + 1) & 1) * 64 * ROW_BYTES);
+      }
+      else jn = base + (((j + 1) ^ jx) << 5) + (uint32_t) ((s & 1) * 64 * ROW_BYTES);
+#pragma unroll
+      for(int hx = 0; hx < 2; hx++)
+#pragma unroll
+        for(int ql = 0; ql < 2; ql++) {
+#pragma unroll
+          for(int ga = 0; ga < 2; ga++)
+#pragma unroll
+            for(int gb = 0; gb < 2; gb++) {
+              const int ai = ((((hx * 2 + ga) * 2 + gb) * 2 + ql) * 2);
+              dmma884(acc[ai], acc[ai + 1], fh[hx][ql], fg[ga][gb]);
+              if(hx == 1 && ql == 1) fg[ga][gb] = lds_f64(jn + hhp_off[ga][gb]);
+            }
+          fh[hx][ql] = lds_f64(jn + hpp_off[hx][ql]);
+        }
+    }
+    if(MODE == 2) {
+      mbar_arrive(smem_u32(&bars[1]));
+      phase ^= 1u;
+    }
+  }
+  double sacc = (double) phase;
+#pragma unroll
+  for(int i = 0; i < 32; i++) sacc += acc[i];
+  out[(int64_t) blockIdx.x * blockDim.x + threadIdx.x] = sacc;
+}
+
 cudaError_t probe_mainloop(int ta, int tb, int warps_per_cta, int ctas_per_sm, int iters, double* tflops) {
   cudaDeviceProp prop;
   int            dev = 0;
   cudaGetDevice(&dev);
   cudaError_t err = cudaGetDeviceProperties(&prop, dev);
   if(err != cudaSuccess) return err;
+  cudaGetLastError();
   void (*k)(double*, int) = nullptr;
   if(ta == 4 && tb == 4) k = mainloop_probe_kernel<4, 4>;
-  else if(ta == 2 && tb == 4) k = mainloop_probe_kernel<2, 4>;
-  else if(ta == 2 && tb == 2) k = mainloop_probe_kernel<2, 2>;
-  else if(ta == 4 && tb == 8) k = mainloop_probe_kernel<4, 8>;
+  else if(ta == 1 && tb == 0) k = mainloop_probe2_kernel<1>;
+  else if(ta == 2 && tb == 0) k = mainloop_probe2_kernel<2>;
+  else if(ta == 3 && tb == 0) k = mainloop_probe2_kernel<3>;
+  else if(ta == 5 && tb == 0) k = mainloop_probe2_kernel<4>;
   else return cudaErrorInvalidValue;
+  if(tb == 0 && warps_per_cta != 4) return cudaErrorInvalidValue;
   // shared memory sized so that exactly ctas_per_sm CTAs fit
-  size_t smem = (size_t) prop.sharedMemPerMultiprocessor / ctas_per_sm - 2048;
+  size_t smem = (size_t) prop.sharedMemPerMultiprocessor / ctas_per_sm - 4096;
   if(smem > prop.sharedMemPerBlockOptin) smem = prop.sharedMemPerBlockOptin;
-  if(smem < 4 * 64 * ROW_BYTES + 1024) return cudaErrorInvalidValue;
+  if(smem < 43 * 1024) return cudaErrorInvalidValue;
   if((err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) return err;
   const int grid = prop.multiProcessorCount * ctas_per_sm, block = 32 * warps_per_cta;
   int       occ  = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, block, smem);
+  if((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, block, smem)) != cudaSuccess) return err;
   if(occ < ctas_per_sm) return cudaErrorLaunchOutOfResources;
   double* out = nullptr;
   if((err = cudaMalloc(&out, sizeof(double) * grid * block)) != cudaSuccess) return err;
@@ -789,7 +869,8 @@ cudaError_t probe_mainloop(int ta, int tb, int warps_per_cta, int ctas_per_sm, i
   cudaEventDestroy(e1);
   cudaFree(out);
   if(err != cudaSuccess) return err;
-  *tflops = (double) grid * warps_per_cta * (double) iters * 4.0 * ta * tb * 512.0 / (best * 1e-3) / 1e12;
+  const double tiles = tb == 0 ? 16.0 : (double) ta * tb;
+  *tflops = (double) grid * warps_per_cta * (double) iters * 4.0 * tiles * 512.0 / (best * 1e-3) / 1e12;
   return cudaGetLastError();
 }
 
