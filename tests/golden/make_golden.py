@@ -25,6 +25,10 @@ CASES = [  # name, noa, nob, nva, nvb, tilesize, restricted, seed
     ("o5v11_ts8", 5, 5, 11, 11, 8, True, 99),
     ("uhf_o3o2_v5v6_ts3", 3, 2, 5, 6, 3, False, 5),
     ("uhf_o4v6_ts4", 4, 4, 6, 6, 4, False, 1234),
+    # the shape of BASELINE configs[0]: H2O cc-pVDZ (5 occupied, 19 virtual orbitals per spin) at the
+    # ccsdt_tilesize of inputs/h2o.json (28): tiles [5][5][19][19], two kernel tasks
+    ("h2o_shape_ts28", 5, 5, 19, 19, 28, True, 2024),
+    ("h2o_shape_ts7", 5, 5, 19, 19, 7, True, 2024),
 ]
 
 
