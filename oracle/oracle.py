@@ -18,6 +18,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "_build", "libccsdt_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libccsdt_ref.so")
+REF_GPU_SO = {"tc": os.path.join(HERE, "_ref", "libccsdt_refgpu_tc.so"),
+              "fma": os.path.join(HERE, "_ref", "libccsdt_refgpu_fma.so")}
 
 _dp = C.POINTER(C.c_double)
 _i64p = C.POINTER(C.c_int64)
@@ -144,11 +146,11 @@ class Oracle:
 class Reference:
     """The reference's own code (oracle/_ref).  Raises FileNotFoundError when it was never built."""
 
-    def __init__(self):
+    def __init__(self, so_path: str = REF_SO):
         build()
-        if not os.path.exists(REF_SO):
-            raise FileNotFoundError(REF_SO)
-        L = C.CDLL(REF_SO)
+        if not os.path.exists(so_path):
+            raise FileNotFoundError(so_path)
+        L = C.CDLL(so_path)
         L.ref_ccsdt_execute.argtypes = [C.c_int] * 4 + [_i64p, _i32p] + [_dp] * 6 + \
             [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _dp, _dp, C.c_int64, _i64p]
         L.ref_ccsdt_execute.restype = C.c_int
@@ -156,7 +158,8 @@ class Reference:
         L.ref_ccsdt_task_info.argtypes = [C.c_int] * 4 + [_i64p, _i32p, C.c_int] + [C.c_int] * 6 + [_i32p] * 4
         L.ref_ccsdt_num_threads.restype = C.c_int
         L.ref_ccsdt_execute_synth.argtypes = [C.c_int] * 4 + [_i64p, _i32p, _dp, _i64p, C.c_uint64, C.c_int,
-                                                               C.c_int, C.c_int, C.c_int64, _dp, _i64p]
+                                                               C.c_int, C.c_int, C.c_int64, _dp, _i64p, _dp,
+                                                               C.c_int64]
         L.ref_ccsdt_execute_synth.restype = C.c_int
         self.L = L
 
@@ -188,9 +191,12 @@ class Reference:
         no = np.ascontiguousarray(n_orb, np.int64)
         out = np.zeros(4)
         n = C.c_int64(0)
+        cap = 1 << 16
+        trace = np.zeros((cap, 10))
         self.L.ref_ccsdt_execute_synth(sp.noa, sp.nob, sp.nva, sp.nvb, _p(kr, _i64p), _p(ks, _i32p), _p(ev, _dp),
                                        _p(no, _i64p), seed, int(is_restricted), tilesize, cache_size, task_limit,
-                                       _p(out, _dp), C.byref(n))
+                                       _p(out, _dp), C.byref(n), _p(trace, _dp), cap)
+        self.last_trace = trace[:min(n.value, cap)].copy()
         return out, int(n.value)
 
     def count_ops(self, sp: Space, is_restricted: bool) -> int:
@@ -212,6 +218,22 @@ class Reference:
                                    int(is_restricted), *[int(x) for x in task[:6]], _p(s1, _i32p),
                                    _p(d1, _i32p), _p(d2, _i32p), _p(cnt, _i32p))
         return s1, d1, d2, cnt
+
+
+class ReferenceGPU(Reference):
+    """The reference's own GPU task function and kernel, compiled unmodified for sm_100a against the shim
+    (oracle/_ref/libccsdt_refgpu_{tc,fma}.so): the on-box GPU comparator of SURVEY.md 8(d).
+    kind "tc" = K1 `fully_fused_kernel_ccsd_t_nvidia_tc_fp64` (ccsd_t_all_fused_gpu.cu:132),
+    kind "fma" = K2 `revised_jk_ccsd_t_fully_fused_kernel` (ccsd_t_all_fused_nontcCuda_Hip_Sycl.cpp:95).
+    Trace records: h1,h2,h3,p4,p5,p6 tile extents, thread blocks, kernel ms, unscaled task E[T], E(T)."""
+
+    def __init__(self, kind: str = "tc"):
+        super().__init__(REF_GPU_SO[kind])
+        self.kind = kind
+        assert int(self.L.ref_ccsdt_gpu_kernel_kind()) == (1 if kind == "tc" else 0)
+
+    def release(self):
+        self.L.ref_ccsdt_gpu_release()
 
 
 # ---------------------------------------------------------------------------------------------

@@ -29,6 +29,7 @@ double ccsdt_d2_v2_GetTime  = 0;
 double genTime              = 0;
 double ccsd_t_data_per_rank = 0;
 
+#ifndef USE_CUDA
 // 1) the reference CPU task function under its own name
 #include "exachem/cc/ccsd_t/ccsd_t_all_fused_cpu.hpp"
 
@@ -67,6 +68,140 @@ void traced_total_fused_ccsd_t_cpu(
 #define total_fused_ccsd_t_cpu traced_total_fused_ccsd_t_cpu
 #include "exachem/cc/ccsd_t/ccsd_t_fused_driver.hpp"
 #undef total_fused_ccsd_t_cpu
+
+#else // USE_CUDA: GPU comparator build (nvcc -x cu -DUSE_CUDA [-DUSE_NV_TC]) ------------------------------
+// Tracing interposer around the reference's kernel LAUNCHER (the kernel, its constant-memory uploads and
+// its launch configuration stay the reference's own): the macro renames the launcher that
+// ccsd_t_all_fused.hpp declares and calls; the renamed template is defined here, brackets the real
+// launcher with CUDA events on the reference's stream, reads the per-block partial energies back and
+// records (extents, blocks, kernel ms, unscaled task energies).
+struct TraceRec {
+  int64_t h1, h2, h3, p4, p5, p6, nblocks;
+  double  kernel_ms, e1_task, e2_task;
+};
+static std::vector<TraceRec> g_trace;
+static int                   g_trace_skip_compute = 0;
+static int64_t               g_trace_limit        = -1;
+struct StopExecute {}; // thrown out of `execute` once task_limit kernel tasks ran (sampling big shapes)
+
+#include "exachem/cc/ccsd_t/ccsd_t_common.hpp"
+#if defined(USE_NV_TC)
+// the real launcher, explicit instantiation at ccsd_t_all_fused_gpu.cu:2682
+template<typename T>
+void ccsd_t_fully_fused_nvidia_tc_fp64(gpuStream_t&, size_t, size_t, size_t, size_t, size_t, size_t, size_t, T*, T*,
+                                       T*, T*, T*, T*, int*, int*, int*, int*, int*, size_t, size_t, size_t,
+                                       size_t, size_t, size_t, size_t, size_t, T*, T*, T*, T*, T*, T*, T*,
+                                       event_ptr_t);
+#define REAL_LAUNCHER ccsd_t_fully_fused_nvidia_tc_fp64
+#else
+// the real launcher, explicit instantiation at ccsd_t_all_fused_nontcCuda_Hip_Sycl.cpp:2922
+template<typename T>
+void fully_fused_ccsd_t_gpu(gpuStream_t&, size_t, size_t, size_t, size_t, size_t, size_t, size_t, T*, T*, T*, T*,
+                            T*, T*, int*, int*, int*, int*, int*, int*, size_t, size_t, size_t, size_t, size_t,
+                            size_t, size_t, size_t, T*, T*, T*, T*, T*, T*, T*, event_ptr_t);
+#define REAL_LAUNCHER fully_fused_ccsd_t_gpu
+#endif
+
+static void trace_before(gpuStream_t& stream, cudaEvent_t* e0, cudaEvent_t* e1) {
+  if(g_trace_limit >= 0 && (int64_t) g_trace.size() >= g_trace_limit) {
+    cudaStreamSynchronize(stream.first);
+    throw StopExecute{};
+  }
+  cudaEventCreate(e0);
+  cudaEventCreate(e1);
+  cudaEventRecord(*e0, stream.first);
+}
+static void trace_after(gpuStream_t& stream, cudaEvent_t e0, cudaEvent_t e1, size_t num_blocks,
+                        const double* dev_energies, size_t h1, size_t h2, size_t h3, size_t p4, size_t p5,
+                        size_t p6) {
+  cudaEventRecord(e1, stream.first);
+  cudaError_t err = cudaEventSynchronize(e1);
+  if(err != cudaSuccess) {
+    std::fprintf(stderr, "reference GPU kernel failed: %s\n", cudaGetErrorString(err));
+    std::exit(100);
+  }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  std::vector<double> part(2 * num_blocks);
+  cudaMemcpy(part.data(), dev_energies, sizeof(double) * 2 * num_blocks, cudaMemcpyDeviceToHost);
+  double a = 0, b = 0;
+  for(size_t i = 0; i < num_blocks; i++) a += part[i], b += part[i + num_blocks];
+  g_trace.push_back({(int64_t) h1, (int64_t) h2, (int64_t) h3, (int64_t) p4, (int64_t) p5, (int64_t) p6,
+                     (int64_t) num_blocks, (double) ms, a, b});
+}
+
+#if defined(USE_NV_TC)
+#define ccsd_t_fully_fused_nvidia_tc_fp64 traced_gpu_launcher
+#else
+#define fully_fused_ccsd_t_gpu traced_gpu_launcher
+#endif
+#include "exachem/cc/ccsd_t/ccsd_t_fused_driver.hpp"
+#undef ccsd_t_fully_fused_nvidia_tc_fp64
+#undef fully_fused_ccsd_t_gpu
+
+// definition of the renamed launcher template that ccsd_t_all_fused.hpp (:36 / :58) declared above
+#if defined(USE_NV_TC)
+template<typename T>
+void traced_gpu_launcher(gpuStream_t& stream, size_t numBlks, size_t size_h3, size_t size_h2, size_t size_h1,
+                         size_t size_p6, size_t size_p5, size_t size_p4, T* a0, T* a1, T* a2, T* a3, T* a4, T* a5,
+                         int* i0, int* i1, int* i2, int* i3, int* i4, size_t z0, size_t z1, size_t z2, size_t z3,
+                         size_t z4, size_t z5, size_t z6, size_t z7, T* e0p, T* e1p, T* e2p, T* e3p, T* e4p,
+                         T* e5p, T* dev_energies, event_ptr_t done_copy) {
+  if(g_trace_skip_compute) return;
+  cudaEvent_t e0, e1;
+  trace_before(stream, &e0, &e1);
+  REAL_LAUNCHER<T>(stream, numBlks, size_h3, size_h2, size_h1, size_p6, size_p5, size_p4, a0, a1, a2, a3, a4, a5,
+                   i0, i1, i2, i3, i4, z0, z1, z2, z3, z4, z5, z6, z7, e0p, e1p, e2p, e3p, e4p, e5p, dev_energies,
+                   done_copy);
+  trace_after(stream, e0, e1, numBlks, dev_energies, size_h1, size_h2, size_h3, size_p4, size_p5, size_p6);
+}
+#else
+template<typename T>
+void traced_gpu_launcher(gpuStream_t& stream, size_t num_blocks, size_t size_h1, size_t size_h2, size_t size_h3,
+                         size_t size_p4, size_t size_p5, size_t size_p6, T* a0, T* a1, T* a2, T* a3, T* a4, T* a5,
+                         int* i0, int* i1, int* i2, int* i3, int* i4, int* i5, size_t z0, size_t z1, size_t z2,
+                         size_t z3, size_t z4, size_t z5, size_t z6, size_t z7, T* e0p, T* e1p, T* e2p, T* e3p,
+                         T* e4p, T* e5p, T* dev_energies, event_ptr_t done_copy) {
+  if(g_trace_skip_compute) return;
+  cudaEvent_t e0, e1;
+  trace_before(stream, &e0, &e1);
+  REAL_LAUNCHER<T>(stream, num_blocks, size_h1, size_h2, size_h3, size_p4, size_p5, size_p6, a0, a1, a2, a3, a4,
+                   a5, i0, i1, i2, i3, i4, i5, z0, z1, z2, z3, z4, z5, z6, z7, e0p, e1p, e2p, e3p, e4p, e5p,
+                   dev_energies, done_copy);
+  trace_after(stream, e0, e1, num_blocks, dev_energies, size_h1, size_h2, size_h3, size_p4, size_p5, size_p6);
+}
+#endif
+#endif // USE_CUDA
+
+// trace record -> 10 doubles.  CPU build: h1,h2,h3,p4,p5,p6 tile ids, taskid, factor, energy_l[0..1]
+// after the task.  GPU build: h1,h2,h3,p4,p5,p6 tile EXTENTS, thread blocks, kernel ms (CUDA events
+// around the reference launcher), unscaled task energies (sum of the kernel's per-block partials).
+#ifndef USE_CUDA
+static void trace_record_out(const TraceRec& r, double* o) {
+  o[0] = (double) r.h1, o[1] = (double) r.h2, o[2] = (double) r.h3, o[3] = (double) r.p4;
+  o[4] = (double) r.p5, o[5] = (double) r.p6, o[6] = (double) r.taskid, o[7] = r.factor;
+  o[8] = r.e1_after, o[9] = r.e2_after;
+}
+#define REF_TRY
+#define REF_CATCH(e1, e2, tw, tt)
+#else
+static void trace_record_out(const TraceRec& r, double* o) {
+  o[0] = (double) r.h1, o[1] = (double) r.h2, o[2] = (double) r.h3, o[3] = (double) r.p4;
+  o[4] = (double) r.p5, o[5] = (double) r.p6, o[6] = (double) r.nblocks, o[7] = r.kernel_ms;
+  o[8] = r.e1_task, o[9] = r.e2_task;
+}
+// a sampled run leaves `execute` by exception: energies are then not available (NaN), the device pool
+// and pinned buffers of that call stay allocated until ref_ccsdt_gpu_release()
+#define REF_TRY try
+#define REF_CATCH(e1, e2, tw, tt)                                   \
+  catch(const StopExecute&) {                                        \
+    cudaDeviceSynchronize();                                         \
+    e1 = e2 = std::nan("");                                         \
+    tw = tt = 0.0;                                                   \
+  }
+#endif
 
 namespace {
 
@@ -188,9 +323,12 @@ int ref_ccsdt_execute(int noa, int nob, int nva, int nvb, const int64_t* k_range
   {
     Silence quiet;
     // same call as exachem/cc/ccsd_t/ccsd_t.cpp:253-256 (seq_h3b = true)
-    std::tie(e1, e2, tw, tt) =
-      drv.execute(chem_env, ec, s.k_spin, MO, d_t1, d_t2, d_v2, k_evl, 0.0, is_restricted != 0,
-                  cache_s1t, cache_s1v, cache_d1t, cache_d1v, cache_d2t, cache_d2v, true);
+    REF_TRY {
+      std::tie(e1, e2, tw, tt) =
+        drv.execute(chem_env, ec, s.k_spin, MO, d_t1, d_t2, d_v2, k_evl, 0.0, is_restricted != 0,
+                    cache_s1t, cache_s1v, cache_d1t, cache_d1v, cache_d2t, cache_d2v, true);
+    }
+    REF_CATCH(e1, e2, tw, tt)
   }
   out[0] = e1;
   out[1] = e2;
@@ -201,16 +339,7 @@ int ref_ccsdt_execute(int noa, int nob, int nva, int nvb, const int64_t* k_range
     for(int64_t i = 0; i < (int64_t) g_trace.size() && i < trace_cap; i++) {
       const TraceRec& r    = g_trace[i];
       double*         o    = trace_out + 10 * i;
-      o[0]                 = (double) r.h1;
-      o[1]                 = (double) r.h2;
-      o[2]                 = (double) r.h3;
-      o[3]                 = (double) r.p4;
-      o[4]                 = (double) r.p5;
-      o[5]                 = (double) r.p6;
-      o[6]                 = (double) r.taskid;
-      o[7]                 = r.factor;
-      o[8]                 = r.e1_after;
-      o[9]                 = r.e2_after;
+      trace_record_out(r, o);
     }
   }
   return 0;
@@ -255,6 +384,21 @@ int ref_ccsdt_task_info(int noa, int nob, int nva, int nvb, const int64_t* k_ran
                                    comm);
   return 0;
 }
+
+#ifdef USE_CUDA
+// 1 = DMMA kernel K1 (ccsd_t_all_fused_gpu.cu), 0 = FMA kernel K2 (ccsd_t_all_fused_nontcCuda_Hip_Sycl.cpp)
+int ref_ccsdt_gpu_kernel_kind() {
+#if defined(USE_NV_TC)
+  return 1;
+#else
+  return 0;
+#endif
+}
+void ref_ccsdt_gpu_release() {
+  cudaDeviceSynchronize();
+  RMMMemoryManager::getInstance().getDeviceMemoryPool().release();
+}
+#endif
 
 int ref_ccsdt_num_threads() {
 #ifdef _OPENMP
@@ -341,7 +485,7 @@ extern "C" {
 int ref_ccsdt_execute_synth(int noa, int nob, int nva, int nvb, const int64_t* k_range,
                             const int32_t* k_spin, const double* evl, const int64_t* n_orb, uint64_t seed,
                             int is_restricted, int tilesize, int cache_size, int64_t task_limit,
-                            double* out, int64_t* n_trace) {
+                            double* out, int64_t* n_trace, double* trace_out, int64_t trace_cap) {
   Space            s  = make_space(noa, nob, nva, nvb, k_range, k_spin);
   TiledIndexSpace  MO = make_mo(s, noa, nob, nva, nvb);
   ExecutionContext ec;
@@ -365,12 +509,17 @@ int ref_ccsdt_execute_synth(int noa, int nob, int nva, int nvb, const int64_t* k
   double                      e1, e2, tw, tt;
   {
     Silence quiet;
-    std::tie(e1, e2, tw, tt) = drv.execute(chem_env, ec, s.k_spin, MO, d_t1, d_t2, d_v2, k_evl, 0.0,
-                                           is_restricted != 0, cache_s1t, cache_s1v, cache_d1t, cache_d1v,
-                                           cache_d2t, cache_d2v, true);
+    REF_TRY {
+      std::tie(e1, e2, tw, tt) = drv.execute(chem_env, ec, s.k_spin, MO, d_t1, d_t2, d_v2, k_evl, 0.0,
+                                             is_restricted != 0, cache_s1t, cache_s1v, cache_d1t, cache_d1v,
+                                             cache_d2t, cache_d2v, true);
+    }
+    REF_CATCH(e1, e2, tw, tt)
   }
   out[0] = e1, out[1] = e2, out[2] = tw, out[3] = tt;
   if(n_trace) *n_trace = (int64_t) g_trace.size();
+  if(trace_out)
+    for(int64_t i = 0; i < (int64_t) g_trace.size() && i < trace_cap; i++) trace_record_out(g_trace[i], trace_out + 10 * i);
   return 0;
 }
 }

@@ -235,6 +235,10 @@ std::shared_ptr<Plan<T>> create_plan(const int* perm, int dim, AlphaT alpha, con
 }
 } // namespace hptt
 
+#if defined(USE_CUDA)
+#include "tamm/gpu_streams.hpp" // GPU comparator build only (oracle/_ref/libccsdt_refgpu_*.so)
+#endif
+
 using namespace tamm;
 using std::cout;
 using std::endl;
