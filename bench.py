@@ -259,6 +259,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def set_symmetry(on):
+        ctx.set_options(**dict(opts, symmetry=1 if on else 0))
+
     def step_resident():
         if counter is not None:
             dist.barrier()
@@ -281,8 +284,8 @@ def main():
         t0 = time.perf_counter()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        agg = {"seconds_kernel": 0.0, "seconds_staging": 0.0, "counted_flops": 0.0, "kernel_launches": 0,
-               "h2d_bytes": 0, "d2h_bytes": 0, "tasks_run": 0}
+        agg = {"seconds_kernel": 0.0, "seconds_staging": 0.0, "counted_flops": 0.0, "evaluated_flops": 0.0,
+               "kernel_launches": 0, "h2d_bytes": 0, "d2h_bytes": 0, "tasks_run": 0}
         e = None
         for _ in range(steps):
             e1, e2, st = fn()
@@ -309,6 +312,12 @@ def main():
         sampler.start()
     dt, agg, energies = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    # the same step with the symmetry reduction switched off (every CTA box evaluated, as the reference does):
+    # the number that is comparable with the reference's kernels box for box
+    n_off = max(1, min(args.steps, 2))
+    set_symmetry(False)
+    dt_off, agg_off, energies_off = timed(step_resident, n_off, 1)
+    set_symmetry(True)
 
     if host is not None:
         n2 = max(1, min(args.steps, 3))
@@ -327,7 +336,8 @@ def main():
     if rank == 0:
         value = agg["flops_all"] / dt / 1e12
         peak = peaks["dmma"]
-        kernel_tf = agg["counted_flops"] / max(agg["seconds_kernel"], 1e-12) / 1e12
+        kernel_tf = agg["evaluated_flops"] / max(agg["seconds_kernel"], 1e-12) / 1e12
+        kernel_tf_off = agg_off["counted_flops"] / max(agg_off["seconds_kernel"], 1e-12) / 1e12
         traffic = NCU_TRAFFIC[wl]
         line = {
             "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -344,6 +354,19 @@ def main():
                        "cta_box": args.sub or "default (2,2,2,8,8,8), 3 CTAs/SM"},
             "t_wall_s_per_step": dt / args.steps,
             "fraction_of_fp64_peak": value / (world * peak),
+            "symmetry": {
+                "what": "when two hole (particle) tiles of a task coincide the summand is symmetric under exchange of the "
+                        "two indices, so the fused kernel evaluates only CTA boxes with ascending box coordinates and "
+                        "weights them (options.symmetry, default on); `value` counts flops as the reference does "
+                        "(every element), so it can exceed the FP64 peak",
+                "evaluated_fraction": agg["evaluated_flops"] / max(agg["counted_flops"], 1.0),
+                "value_symmetry_off": agg_off["flops_all"] / dt_off / 1e12,
+                "ms_per_step_symmetry_off": dt_off / n_off * 1e3,
+                "fraction_of_fp64_peak_symmetry_off": agg_off["flops_all"] / dt_off / 1e12 / (world * peak),
+                "kernel_tflops_symmetry_off": kernel_tf_off,
+                "max_abs_energy_diff_on_vs_off": max(abs(energies[0] - energies_off[0]), abs(energies[1] - energies_off[1])),
+                "max_rel_energy_diff_on_vs_off": max(abs(energies[0] - energies_off[0]) / abs(energies_off[0]),
+                                                     abs(energies[1] - energies_off[1]) / abs(energies_off[1]))},
             "energies": {"E[T]": energies[0], "E(T)": energies[1]},
             "roofline": {"bound": "tensor", "achieved": kernel_tf, "peak": peak, "unit": "TFLOP/s",
                          "frac": kernel_tf / peak, "traffic": traffic["bytes"],
@@ -352,8 +375,10 @@ def main():
                          "peak_source": "measured in this run by ccsdt_probe_fp64_peak: register-resident DMMA.8x8x4 issue loop "
                                         "(MEASURED_PEAKS.json has no FP64 entry; nominal HGX B200 FP64 = 37 TFLOP/s)",
                          "peaks_measured": peaks,
-                         "achieved_def": "reference-counted flops of this rank's tasks / CUDA-event time of its fused-kernel "
-                                         "launches on their stream (rank 0)"},
+                         "achieved_def": "reference-counted flops of the t3 elements this rank's fused-kernel launches had to "
+                                         "evaluate (counted flops x CTA boxes evaluated / CTA boxes of the tile; padding not "
+                                         "counted) / CUDA-event time of those launches on their stream (rank 0)",
+                         "achieved_symmetry_off": kernel_tf_off, "frac_symmetry_off": kernel_tf_off / peak},
             "e2e": e2e, "gpu_launches": int(agg["launches_all"]), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -18,14 +18,14 @@ _u8p = C.POINTER(C.c_uint8)
 class Options(C.Structure):
     _fields_ = [("kernel", C.c_int32), ("sub", C.c_int32 * 3), ("stages", C.c_int32),
                 ("ctas_per_sm", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
-                ("overlap", C.c_int32), ("stagger", C.c_int32), ("verbose", C.c_int32)]
+                ("overlap", C.c_int32), ("stagger", C.c_int32), ("verbose", C.c_int32), ("symmetry", C.c_int32)]
 
 
 class Stats(C.Structure):
     _fields_ = [("tasks_run", C.c_int64), ("kernel_launches", C.c_int64), ("counted_flops", C.c_double),
                 ("seconds_total", C.c_double), ("seconds_kernel", C.c_double),
                 ("seconds_staging", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("blocks_fetched", C.c_int64)]
+                ("blocks_fetched", C.c_int64), ("evaluated_flops", C.c_double)]
 
 
 FETCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, _u32p, _dp, C.c_size_t)
@@ -42,6 +42,7 @@ SIGNATURES = {
     "ccsdt_count_ops": (C.c_int, [C.c_int, C.c_int, _i32p, _i64p, C.c_int, C.POINTER(C.c_longdouble)]),
     "ccsdt_partition": (C.c_int, [C.c_int, C.c_int, _i32p, _i64p, C.c_int, C.c_int, _i32p, C.c_int64]),
     "ccsdt_check_memory": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "ccsdt_box_weight": (C.c_int, [C.c_int, _i32p]),
     "ccsdt_set_space": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [_i64p, _i32p, _dp, C.c_int]),
     "ccsdt_put_dense": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "ccsdt_put_block": (C.c_int, [C.c_void_p, C.c_int, _u32p, _dp]),

@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <array>
 #include <map>
 #include <string>
 #include <vector>
@@ -61,6 +62,7 @@ struct StageBuf {
   TaskParams   params;
   int          grid = 0, consumer_warps = 0;
   size_t       smem = 0;
+  double       eval_fraction = 1.0; // boxes evaluated / boxes of the tile (symmetry)
 };
 
 } // namespace
@@ -98,6 +100,12 @@ struct ccsdt_ctx {
   void*        encode_fn = nullptr;
   int64_t*     task_counter = nullptr; // process-shared dynamic task counter (NULL = static split)
   ccsdt_stats  stats{};
+  // symmetry-reduced box lists (device), keyed by (nbox, brick, nbrick, sym): a handful per job
+  struct BoxList {
+    int32_t* dev = nullptr;
+    int32_t  n   = 0;
+  };
+  std::map<std::array<int, 19>, BoxList> box_lists;
 
   int fail(const std::string& m, int code = 1) {
     err = m;
@@ -651,6 +659,49 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     if(padded > 0x7fffffff) return ctx->fail("task has too many CTA boxes", 7);
     P.nboxes_padded = (int) padded;
     P.box_counter   = b.d_counter;
+    // permutational symmetry of coinciding tiles: evaluate ascending box coordinates only (weights in the kernel)
+    P.sym = 0, P.nlist = 0, P.box_list = nullptr;
+    if(ctx->opt.symmetry) {
+      if(t.t[0] == t.t[1] && P.c[0] == P.c[1]) P.sym |= 1;
+      if(t.t[1] == t.t[2] && P.c[1] == P.c[2]) P.sym |= 2;
+      if(t.t[3] == t.t[4]) P.sym |= 4;
+      if(t.t[4] == t.t[5]) P.sym |= 8;
+    }
+    if(P.sym) {
+      std::array<int, 19> key;
+      for(int i = 0; i < 6; i++) key[i] = P.nbox[i], key[6 + i] = P.brick[i], key[12 + i] = P.nbrick[i];
+      key[18]  = P.sym;
+      auto& bl = ctx->box_lists[key];
+      if(!bl.dev) {
+        std::vector<int32_t> ids;
+        const int            order[6] = {2, 1, 0, 5, 4, 3}; // same decoding as decode_box (ccsdt_kernel_common.cuh)
+        for(int64_t id = 0; id < padded; id++) {
+          int     in[6], bx[6];
+          int64_t r     = id;
+          bool    valid = true;
+          for(int i = 0; i < 6; i++) {
+            const int d = order[i];
+            in[d]       = (int) (r % P.brick[d]);
+            r /= P.brick[d];
+          }
+          for(int i = 0; i < 6; i++) {
+            const int d = order[i];
+            bx[d]       = (int) (r % P.nbrick[d]) * P.brick[d] + in[d];
+            r /= P.nbrick[d];
+            valid &= bx[d] < P.nbox[d];
+          }
+          if(valid && box_weight(P.sym, bx) > 0) ids.push_back((int32_t) id);
+        }
+        bl.n = (int32_t) ids.size();
+        CK(cudaMalloc(&bl.dev, sizeof(int32_t) * std::max<size_t>(ids.size(), 1)));
+        CK(cudaMemcpy(bl.dev, ids.data(), sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice));
+      }
+      P.box_list = bl.dev;
+      P.nlist    = bl.n;
+      nboxes     = bl.n;
+      b.grid     = (int) std::max<int64_t>(1, std::min<int64_t>(nboxes, in_flight));
+    }
+    b.eval_fraction = (double) nboxes / (double) P.nboxes;
     // one box keeps the tensor pipe of an SM busy for (k-steps x 16 DMMA x 16 cycles) / 4 sub-partitions x
     // 4 warps = k-steps x 256 cycles; co-resident CTAs start that far apart (options.stagger, default on)
     int64_t ksteps = 0;
@@ -750,7 +801,7 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
   if(ctx->task_counter) {
     order = ids;
     std::vector<long double> cost(ctx->tasks.size(), 0);
-    for(int64_t id: ids) cost[id] = task_ops(ctx->sp, ctx->tasks[id]);
+    for(int64_t id: ids) cost[id] = task_cost(ctx->sp, ctx->tasks[id], ctx->opt.symmetry != 0);
     std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cost[a] > cost[b]; });
   }
   else if(use_global_split || ctx->opt.nranks <= 1) {
@@ -761,7 +812,7 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
     // static split of this list alone: longest-processing-time greedy, identical on every rank
     std::vector<Task> sub;
     for(int64_t id: ids) sub.push_back(ctx->tasks[id]);
-    const std::vector<int32_t> own = partition_tasks(ctx->sp, sub, ctx->opt.nranks);
+    const std::vector<int32_t> own = partition_tasks(ctx->sp, sub, ctx->opt.nranks, ctx->opt.symmetry != 0);
     for(int64_t k = 0; k < nids; k++)
       if(own[k] == ctx->opt.rank) order.push_back(ids[k]);
   }
@@ -794,7 +845,9 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
       CK(cudaStreamWaitEvent(ctx->s_stage, b.done, 0));
       if(int rc = stage_task(ctx, b, ctx->tasks[ti])) return rc;
       if(int rc = launch_task(ctx, b, j)) return rc;
-      ctx->stats.counted_flops += (double) task_ops(ctx->sp, ctx->tasks[ti]);
+      const double ops = (double) task_ops(ctx->sp, ctx->tasks[ti]);
+      ctx->stats.counted_flops += ops;
+      ctx->stats.evaluated_flops += ops * (ctx->opt.kernel == CCSDT_KERNEL_DMMA ? b.eval_fraction : 1.0);
     }
     const int64_t n = (int64_t) mine.size();
     for(int i = 0; i < nbuf; i++)
@@ -842,6 +895,11 @@ extern "C" {
 
 CCSDT_API const char* ccsdt_last_error(const ccsdt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+int ccsdt_box_weight(int sym, const int32_t box[6]) {
+  const int bi[6] = {box[0], box[1], box[2], box[3], box[4], box[5]};
+  return box_weight(sym, bi);
+}
+
 int ccsdt_default_options(ccsdt_options* o) {
   if(!o) return 1;
   memset(o, 0, sizeof(*o));
@@ -850,6 +908,7 @@ int ccsdt_default_options(ccsdt_options* o) {
   o->nranks  = 1;
   o->overlap = 1;
   o->stagger = 1;
+  o->symmetry = 1;
   return 0;
 }
 
@@ -910,6 +969,8 @@ int ccsdt_destroy(ccsdt_ctx* ctx) {
   if(ctx->d_evl) cudaFree(ctx->d_evl);
   if(ctx->d_task_energy) cudaFree(ctx->d_task_energy);
   if(ctx->d_error) cudaFree(ctx->d_error);
+  for(auto& kv: ctx->box_lists)
+    if(kv.second.dev) cudaFree(kv.second.dev);
   if(ctx->h_fetch) cudaFreeHost(ctx->h_fetch);
   if(ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
   if(ctx->s_stage) cudaStreamDestroy(ctx->s_stage);
@@ -936,7 +997,7 @@ int ccsdt_set_options(ccsdt_ctx* ctx, const ccsdt_options* o) {
   cudaDeviceSynchronize();
   free_pools(ctx); // box shape and overlap change the pool geometry
   ctx->opt = n;
-  if(ctx->have_space) ctx->owner = partition_tasks(ctx->sp, ctx->tasks, ctx->opt.nranks);
+  if(ctx->have_space) ctx->owner = partition_tasks(ctx->sp, ctx->tasks, ctx->opt.nranks, ctx->opt.symmetry != 0);
   return 0;
 }
 
@@ -1018,7 +1079,7 @@ int ccsdt_set_space(ccsdt_ctx* ctx, int noa, int nob, int nva, int nvb, const in
   ctx->sp         = sp;
   ctx->have_space = true;
   ctx->tasks      = enumerate_tasks(sp.noab(), sp.nvab(), sp.k_spin.data(), sp.restricted, &ctx->n_outer);
-  ctx->owner      = partition_tasks(sp, ctx->tasks, ctx->opt.nranks);
+  ctx->owner      = partition_tasks(sp, ctx->tasks, ctx->opt.nranks, ctx->opt.symmetry != 0);
   if(ctx->d_evl) cudaFree(ctx->d_evl);
   CK(cudaMalloc(&ctx->d_evl, sp.evl.size() * 8));
   CK(cudaMemcpy(ctx->d_evl, sp.evl.data(), sp.evl.size() * 8, cudaMemcpyHostToDevice));

@@ -88,7 +88,31 @@ struct alignas(64) TaskParams {
   int32_t     ctas_per_sm;
   int32_t     stages, stage_bytes;
   uint32_t*   error_flag;
+  // Permutational symmetry inside a task (options.symmetry): when two hole (particle) TILES of the task
+  // coincide, the summand d*d/D and d*(d+s)/D is symmetric under exchange of the two element indices
+  // (t3 is antisymmetric in same-spin indices), so only boxes with ascending box coordinates along
+  // coinciding indices are evaluated and their partials are weighted by the number of distinct
+  // permutations (1, 2, 3 or 6 per index family).  sym bits: 0 = h1~h2, 1 = h2~h3, 2 = p4~p5, 3 = p5~p6.
+  // box_list (device, brick-major order of the surviving ids of the padded grid) replaces the id range.
+  int32_t        sym;
+  int32_t        nlist;
+  const int32_t* box_list;
 };
+
+// weight of a box under the task's symmetry bits; 0 = the box is a mirror image and is skipped
+__host__ __device__ inline int box_weight(int sym, const int bi[6]) {
+  int w = 1;
+  for(int f = 0; f < 2; f++) {
+    const int  a = bi[3 * f], b = bi[3 * f + 1], c = bi[3 * f + 2];
+    const bool s01 = (sym >> (2 * f)) & 1, s12 = (sym >> (2 * f + 1)) & 1;
+    if(s01 && a > b) return 0;
+    if(s12 && b > c) return 0;
+    if(s01 && s12) w *= (a < b && b < c) ? 6 : ((a < b || b < c) ? 3 : 1);
+    else if(s01) w *= a < b ? 2 : 1;
+    else if(s12) w *= b < c ? 2 : 1;
+  }
+  return w;
+}
 
 // Panel-build work item: dst[o2][o1][in][k] = scale * src[...]  (or a procedural value)
 struct GatherDesc {

@@ -230,11 +230,37 @@ long double count_ops(const Space& sp) {
   return tot_s1 + tot_d1 + tot_d2;
 }
 
-std::vector<int32_t> partition_tasks(const Space& sp, const std::vector<Task>& tasks, int nranks) {
+double symmetry_fraction(const Space& sp, const Task& t, const int hbox[3], int pbox) {
+  double frac = 1.0;
+  for(int f = 0; f < 2; f++) {
+    int64_t n[3];
+    for(int i = 0; i < 3; i++) {
+      const int64_t box = f == 0 ? hbox[i] : pbox;
+      n[i]              = (sp.k_range[t.t[3 * f + i]] + box - 1) / box;
+    }
+    const bool s01 = t.t[3 * f] == t.t[3 * f + 1] && (f == 1 || hbox[0] == hbox[1]);
+    const bool s12 = t.t[3 * f + 1] == t.t[3 * f + 2] && (f == 1 || hbox[1] == hbox[2]);
+    const double all = (double) n[0] * n[1] * n[2];
+    if(all <= 0) continue;
+    double keep = all;
+    if(s01 && s12) keep = (double) n[0] * (n[0] + 1) * (n[0] + 2) / 6.0;
+    else if(s01) keep = (double) n[0] * (n[0] + 1) / 2.0 * n[2];
+    else if(s12) keep = (double) n[0] * n[1] * (n[1] + 1) / 2.0;
+    frac *= keep / all;
+  }
+  return frac;
+}
+
+long double task_cost(const Space& sp, const Task& t, bool symmetry) {
+  const int hbox[3] = {2, 2, 2};
+  return task_ops(sp, t) * (symmetry ? (long double) symmetry_fraction(sp, t, hbox, 8) : 1.0L);
+}
+
+std::vector<int32_t> partition_tasks(const Space& sp, const std::vector<Task>& tasks, int nranks, bool symmetry) {
   std::vector<int32_t> owner(tasks.size(), 0);
   if(nranks <= 1) return owner;
   std::vector<long double> cost(tasks.size());
-  for(size_t i = 0; i < tasks.size(); i++) cost[i] = task_ops(sp, tasks[i]);
+  for(size_t i = 0; i < tasks.size(); i++) cost[i] = task_cost(sp, tasks[i], symmetry);
   std::vector<size_t> order(tasks.size());
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cost[a] > cost[b]; });

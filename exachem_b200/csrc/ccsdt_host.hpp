@@ -75,7 +75,15 @@ void task_terms(const Space& sp, const Task& t, uint8_t* s1_on, uint8_t* d1_on, 
 long double task_ops(const Space& sp, const Task& t);
 long double count_ops(const Space& sp);
 
-// static split: longest-processing-time greedy on task_ops; owner[i] in [0,nranks)
-std::vector<int32_t> partition_tasks(const Space& sp, const std::vector<Task>& tasks, int nranks);
+// Fraction of a task's CTA boxes the fused kernel evaluates when it exploits the permutational symmetry of
+// coinciding tiles (boxes of hbox[i] elements per hole index and pbox per particle index): with n boxes
+// along two coinciding indices n(n+1)/2 of n^2 survive, along three n(n+1)(n+2)/6 of n^3.
+double symmetry_fraction(const Space& sp, const Task& t, const int hbox[3], int pbox);
+// cost model of one task: task_ops, times symmetry_fraction for the default boxes (2,2,2,8,8,8) if asked
+long double task_cost(const Space& sp, const Task& t, bool symmetry);
+
+// static split: longest-processing-time greedy on task_cost; owner[i] in [0,nranks)
+std::vector<int32_t> partition_tasks(const Space& sp, const std::vector<Task>& tasks, int nranks,
+                                     bool symmetry = true);
 
 } // namespace ccsdt

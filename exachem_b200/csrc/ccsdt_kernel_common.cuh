@@ -105,13 +105,14 @@ struct Ring {
 
 struct BoxCoord {
   int off[6]; // element offset of the box inside the tile, per index id
+  int weight; // permutation multiplicity of the box (TaskParams::sym), 1 without symmetry
 };
 
 // id -> box coordinates; false when the id is padding of the brick grid.  Inside a brick and across
 // bricks h3 runs fastest, then h2, h1, p6, p5, p4.
 __device__ __forceinline__ bool decode_box(const TaskParams& p, int id, BoxCoord& b) {
   const int order[6] = {2, 1, 0, 5, 4, 3};
-  int       in[6], r = id;
+  int       in[6], bx[6], r = id;
   bool      valid = true;
 #pragma unroll
   for(int i = 0; i < 6; i++) {
@@ -125,9 +126,11 @@ __device__ __forceinline__ bool decode_box(const TaskParams& p, int id, BoxCoord
     const int bi = (r % p.nbrick[d]) * p.brick[d] + in[d];
     r /= p.nbrick[d];
     valid &= bi < p.nbox[d];
+    bx[d]    = bi;
     b.off[d] = bi * (d < 3 ? p.c[d] : PBOX);
   }
-  return valid;
+  b.weight = p.sym ? box_weight(p.sym, bx) : 1;
+  return valid && b.weight > 0;
 }
 
 } // namespace ccsdt

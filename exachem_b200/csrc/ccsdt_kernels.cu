@@ -395,6 +395,11 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
       if(lane == 0) {
         for(;;) {
           id = (int) atomicAdd(p.box_counter, 1u);
+          if(p.box_list) { // symmetry-reduced task: dense list of the surviving ids
+            id = id < p.nlist ? __ldg(p.box_list + id) : -1;
+            if(id >= 0) decode_box(p, id, bc);
+            break;
+          }
           if(id >= p.nboxes_padded) {
             id = -1;
             break;
@@ -568,8 +573,9 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
     if(tid == 0) {
       double a = 0.0, b = 0.0;
       for(int i = 0; i < ncw; i++) a += red[0][i], b += red[1][i];
-      p.partial[2 * (int64_t) box]     = a;
-      p.partial[2 * (int64_t) box + 1] = b;
+      const double w = (double) boxq[seq % BOXQ].bc.weight; // the entry outlives the box (see BOXQ)
+      p.partial[2 * (int64_t) box]     = w * a;
+      p.partial[2 * (int64_t) box + 1] = w * b;
     }
     named_bar_sync(1, ncw * 32); // red[] may be overwritten by the next box
   }

@@ -77,6 +77,11 @@ typedef struct ccsdt_options {
   int32_t overlap;       /* 1 = stage task n+1 while task n computes (default), 0 = serial */
   int32_t stagger;       /* 1 = de-phase the CTAs sharing an SM by a fraction of a box time (default), 0 = off */
   int32_t verbose;
+  int32_t symmetry;      /* 1 (default) = when two hole (particle) tiles of a task coincide, evaluate only the CTA
+                            boxes with ascending box coordinates along those indices and weight them by their
+                            permutation multiplicity (t3 is antisymmetric in same-spin indices, so d*d/D and
+                            d*(d+s)/D are symmetric; the reference evaluates every element and lets `factor`
+                            undo the over-count, ccsd_t_fused_driver.hpp:387-395); 0 = evaluate every box */
 } ccsdt_options;
 
 typedef struct ccsdt_stats {
@@ -88,6 +93,8 @@ typedef struct ccsdt_stats {
   double  seconds_staging;    /* CUDA-event time of the panel-build launches (sum) */
   int64_t h2d_bytes, d2h_bytes;
   int64_t blocks_fetched;     /* fetch-callback invocations */
+  double  evaluated_flops;    /* counted_flops x (CTA boxes evaluated / CTA boxes of the tile): what the fused kernel
+                                 had to execute after the symmetry reduction (== counted_flops with symmetry = 0) */
 } ccsdt_stats;
 
 /* delivers one UNSORTED row-major block, i.e. what Tensor<T>::get(bid, buf) returns */
@@ -113,6 +120,10 @@ CCSDT_API int     ccsdt_partition(int noab, int nvab, const int32_t* k_spin, con
                         int is_restricted, int nranks, int32_t* owner /* one per kernel task */,
                         int64_t cap);
 CCSDT_API int     ccsdt_check_memory(int tilesize, int nbf, size_t gpu_bytes, size_t* required);
+/* permutation weight the fused kernel gives CTA box `box` (box coordinates along h1,h2,h3,p4,p5,p6) under
+ * symmetry bits `sym` (bit 0: tiles h1b==h2b, 1: h2b==h3b, 2: p4b==p5b, 3: p5b==p6b); 0 = the box is the
+ * mirror image of an evaluated one and is skipped.  Summed over a tile's boxes the weights count every box once. */
+CCSDT_API int     ccsdt_box_weight(int sym, const int32_t box[6]);
 
 /* problem definition */
 CCSDT_API int ccsdt_set_space(ccsdt_ctx* ctx, int noa, int nob, int nva, int nvb, const int64_t* k_range,

@@ -325,3 +325,49 @@ def test_task_list_subset_and_order_independent():
         ctx.close()
     assert np.array_equal(pt, full[3][ids]) and st["tasks_run"] == len(ids)
     assert abs(e1 - full[3][ids, 0].sum()) < 1e-12
+
+
+@pytest.mark.parametrize("cfg", [(6, 6, 17, 17, 40, True, 3),      # one tile per spin block: every ααα task is 6x6-fold symmetric
+                                 (9, 9, 21, 21, 8, True, 4),       # mixed: equal pairs, equal triples, distinct tiles, ragged tails
+                                 (5, 3, 9, 12, 4, False, 5),       # unrestricted, unequal alpha/beta counts (bbb / abb tasks too)
+                                 (7, 7, 13, 13, 5, True, 6)])
+def test_symmetry_reduction_equals_full_evaluation(orc, cfg):
+    """options.symmetry (default on) skips the CTA boxes that are mirror images under exchange of indices whose
+    TILES coincide and weights the rest; per task it must give what the full evaluation and the oracle give."""
+    oa, ob, va, vb, ts, restricted, seed = cfg
+    sp, osp = drv.setup_mo_space(oa, ob, va, vb, ts), orc.tiles(oa, ob, va, vb, ts)
+    T = syn.dense_all(syn.Orbitals(oa, ob, va, vb), seed)
+    ref = orc.run(osp, T, restricted, per_task=True)
+    on = run_gpu(sp, T, restricted, symmetry=1)
+    off = run_gpu(sp, T, restricted, symmetry=0)
+    for r in (on, off):
+        assert _close(r[0], ref[0]) and _close(r[1], ref[1])
+        assert np.allclose(r[3], ref[2], rtol=1e-11, atol=ATOL)
+    assert off[2]["evaluated_flops"] == off[2]["counted_flops"] == on[2]["counted_flops"]
+    assert on[2]["evaluated_flops"] < 0.8 * on[2]["counted_flops"]
+    # other CTA boxes (hole box 2,2,4: the h2~h3 symmetry is then not usable) and the diagnostic kernel
+    alt = run_gpu(sp, T, restricted, symmetry=1, sub=(1, 1, 2))
+    assert np.allclose(alt[3], ref[2], rtol=1e-11, atol=ATOL)
+
+
+def test_symmetry_reduction_headline_shape():
+    """(60,500) ts32 on device-generated tensors: task 0 (tiles 0,0,0 | 4,4,4: 36-fold symmetric) and an aab task
+    with h1b == h2b, symmetry on vs off"""
+    no, nv, ts = 60, 500, 32
+    sp = drv.setup_mo_space(no, no, nv, nv, ts)
+    evl = syn.Orbitals(no, no, nv, nv).orbital_energies()
+    tasks, _, _ = drv.enumerate_tasks(sp, True)
+    aab = next(i for i, t in enumerate(tasks) if t[0] == t[1] and sp.k_spin[t[2]] == 2 and t[3] != t[4])
+    res = {}
+    for s in (1, 0):
+        ctx = drv.Context(0)
+        try:
+            ctx.set_options(symmetry=s)
+            ctx.set_space(sp, evl, True)
+            ctx.set_synthetic(1234)
+            res[s] = ctx.run_tasks([0, aab], per_task=True)
+        finally:
+            ctx.close()
+    assert np.allclose(res[1][3], res[0][3], rtol=1e-11, atol=0)
+    assert res[1][2]["evaluated_flops"] < 0.35 * res[0][2]["evaluated_flops"]
+    assert res[1][2]["seconds_kernel"] < 0.5 * res[0][2]["seconds_kernel"]

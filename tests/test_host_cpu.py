@@ -91,3 +91,27 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt \
                     and "ccsdt_oracle" not in txt and "libccsdt_ref" not in txt, os.path.join(dirpath, f)
+
+
+@pytest.mark.parametrize("sym", range(16))
+def test_box_weights_count_every_box_once(sym):
+    """symmetry reduction of the fused kernel (options.symmetry): over the boxes of a tile whose coinciding
+    indices have equal box counts, the weights of the surviving boxes add up to the number of boxes"""
+    import ctypes as C
+    import itertools
+    L = _lib.load()
+    nh, nh3, np_, np6 = 4, 3, 3, 2
+    # coinciding indices must have the same number of boxes
+    n = [nh, nh if sym & 1 else 5, 0, np_, np_ if sym & 4 else 4, 0]
+    n[2] = n[1] if sym & 2 else nh3
+    n[5] = n[4] if sym & 8 else np6
+    total, kept = 0, 0
+    for box in itertools.product(*[range(k) for k in n]):
+        b = (C.c_int32 * 6)(*box)
+        w = L.ccsdt_box_weight(sym, b)
+        total += w
+        kept += w > 0
+        assert w in (0, 1, 2, 3, 6, 4, 9, 12, 18, 36)
+    assert total == int(np.prod(n))
+    if sym:
+        assert kept < int(np.prod(n))
