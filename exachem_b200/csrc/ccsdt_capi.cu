@@ -48,7 +48,7 @@ const char* kKinds[5] = {"vo", "vvoo", "oovv", "ooov", "ovvv"};
 struct StageBuf {
   PoolGeom     geom{};
   double*      s1_a = nullptr; // [9][THp][TPp]
-  double*      s1_b = nullptr; // [9][TPp][TPp][THp][THp]
+  double*      s1_b = nullptr; // [9][THp][THp][TPp][TPp]
   GatherDesc*  d_descs = nullptr;
   GatherDesc*  h_descs = nullptr; // pinned
   int          desc_cap = 0;
@@ -63,6 +63,7 @@ struct StageBuf {
   int          grid = 0, consumer_warps = 0;
   size_t       smem = 0;
   double       eval_fraction = 1.0; // boxes evaluated / boxes of the tile (symmetry)
+  cudaStream_t cs = nullptr;        // compute stream of this buffer (see run_task_list)
 };
 
 } // namespace
@@ -96,7 +97,9 @@ struct ccsdt_ctx {
   double*      d_task_energy = nullptr;
   int64_t      task_energy_cap = 0;
   uint32_t*    d_error = nullptr;
-  cudaStream_t s_compute = nullptr, s_stage = nullptr;
+  cudaStream_t s_compute = nullptr, s_compute2 = nullptr, s_stage = nullptr;
+  cudaEvent_t  ev_base = nullptr;   // start of the current run: kernel intervals are placed on its time line
+  double       kernel_busy_until = 0.0; // end (ms after ev_base) of the union of fused-kernel intervals so far
   void*        encode_fn = nullptr;
   int64_t*     task_counter = nullptr; // process-shared dynamic task counter (NULL = static split)
   ccsdt_stats  stats{};
@@ -566,7 +569,7 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
   for(int i = 0; i < nterms; i++)
     if(terms[i].layout_y) P.term[w++] = terms[i];
 
-  // ---- s1 terms: a = sign*T1[pa,hx] as [hx][pa], b = v2ijab[hz,hy,pc,pb] as [pb][pc][hy][hz] ----
+  // ---- s1 terms: a = sign*T1[pa,hx] as [hx][pa], b = v2ijab[hz,hy,pc,pb] as [hy][hz][pb][pc] ----
   P.ns1 = 0;
   for(int k = 0; k < 9; k++) {
     if(!s1_enabled(sp, t, k)) continue;
@@ -581,10 +584,12 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     sd.pa       = T.pa;
     sd.sa[T.hx] = g.TPp;
     sd.sa[T.pa] = 1;
-    sd.sb[T.pb] = g.TPp * g.THp * g.THp;
-    sd.sb[T.pc] = g.THp * g.THp;
-    sd.sb[T.hy] = g.THp;
-    sd.sb[T.hz] = 1;
+    // particle indices innermost: the 32 lanes of a warp differ in particle offsets only, so one warp-wide
+    // load of b touches at most 8 rows of 64 bytes (it touched 32 lines with the holes innermost)
+    sd.sb[T.hy] = g.THp * g.TPp * g.TPp;
+    sd.sb[T.hz] = g.TPp * g.TPp;
+    sd.sb[T.pb] = g.TPp;
+    sd.sb[T.pc] = 1;
     SrcSpec a{};
     a.tensor              = CCSDT_T1;
     const uint32_t abid[4] = {vt(T.pa), tile(T.hx), 0, 0};
@@ -598,10 +603,10 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     v.tensor               = CCSDT_V_IJAB;
     const uint32_t vbid[4] = {tile(T.hz), tile(T.hy), vt(T.pc), vt(T.pb)};
     memcpy(v.bid, vbid, sizeof(vbid));
-    const int vdim[4] = {3, 2, 1, 0}; // dst (pb, pc, hy, hz)
+    const int vdim[4] = {1, 0, 3, 2}; // dst (hy, hz, pb, pc)
     memcpy(v.dim_of, vdim, sizeof(vdim));
     v.scale               = 1.0;
-    const int64_t ds_b[4] = {(int64_t) g.TPp * g.THp * g.THp, (int64_t) g.THp * g.THp, g.THp, 1};
+    const int64_t ds_b[4] = {(int64_t) g.THp * g.TPp * g.TPp, (int64_t) g.TPp * g.TPp, g.TPp, 1};
     if(int rc = add_gather(ctx, b, nd, max_elems, pb, ds_b, v)) return rc;
   }
 
@@ -714,7 +719,7 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
   }
   b.nparts = need_partial;
   if(need_partial > b.partial_cap) {
-    CK(cudaStreamSynchronize(ctx->s_compute));
+    CK(cudaStreamSynchronize(b.cs));
     if(b.d_partial) CK(cudaFree(b.d_partial));
     b.partial_cap = need_partial + need_partial / 4 + 64;
     CK(cudaMalloc(&b.d_partial, (size_t) b.partial_cap * 16));
@@ -741,29 +746,29 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
 }
 
 int launch_task(ccsdt_ctx* ctx, StageBuf& b, int64_t slot) {
-  CK(cudaStreamWaitEvent(ctx->s_compute, b.staged, 0));
+  CK(cudaStreamWaitEvent(b.cs, b.staged, 0));
   if(ctx->opt.kernel == CCSDT_KERNEL_SIMPLE) {
     int nparts = 0;
-    CK(cudaEventRecord(b.k0, ctx->s_compute));
-    CK(launch_fused_simple(b.params, ctx->s_compute, &nparts));
-    CK(cudaEventRecord(b.k1, ctx->s_compute));
+    CK(cudaEventRecord(b.k0, b.cs));
+    CK(launch_fused_simple(b.params, b.cs, &nparts));
+    CK(cudaEventRecord(b.k1, b.cs));
   }
   else if(b.params.nterms == 0) {
     // no doubles contraction is enabled: d = 0 for every element, so E[T] and E(T) of the task are exactly 0
-    CK(cudaEventRecord(b.k0, ctx->s_compute));
-    CK(cudaMemsetAsync(b.d_partial, 0, (size_t) b.nparts * 16, ctx->s_compute));
-    CK(cudaEventRecord(b.k1, ctx->s_compute));
+    CK(cudaEventRecord(b.k0, b.cs));
+    CK(cudaMemsetAsync(b.d_partial, 0, (size_t) b.nparts * 16, b.cs));
+    CK(cudaEventRecord(b.k1, b.cs));
   }
   else {
     // ids of the padded brick grid that are not boxes are never written: their partials stay zero
-    CK(cudaMemsetAsync(b.d_partial, 0, (size_t) b.nparts * 16, ctx->s_compute));
-    CK(cudaMemsetAsync(b.d_counter, 0, 4 * COUNTER_WORDS, ctx->s_compute));
-    CK(cudaEventRecord(b.k0, ctx->s_compute));
-    CK(launch_fused_dmma(b.params, b.grid, b.consumer_warps, b.smem, ctx->s_compute));
-    CK(cudaEventRecord(b.k1, ctx->s_compute));
+    CK(cudaMemsetAsync(b.d_partial, 0, (size_t) b.nparts * 16, b.cs));
+    CK(cudaMemsetAsync(b.d_counter, 0, 4 * COUNTER_WORDS, b.cs));
+    CK(cudaEventRecord(b.k0, b.cs));
+    CK(launch_fused_dmma(b.params, b.grid, b.consumer_warps, b.smem, b.cs));
+    CK(cudaEventRecord(b.k1, b.cs));
   }
-  CK(launch_reduce_partials(b.d_partial, (int) b.nparts, ctx->d_task_energy + 2 * slot, ctx->s_compute));
-  CK(cudaEventRecord(b.done, ctx->s_compute));
+  CK(launch_reduce_partials(b.d_partial, (int) b.nparts, ctx->d_task_energy + 2 * slot, b.cs));
+  CK(cudaEventRecord(b.done, b.cs));
   b.timing_pending = true;
   ctx->stats.kernel_launches += 2;
   return 0;
@@ -772,9 +777,15 @@ int launch_task(ccsdt_ctx* ctx, StageBuf& b, int64_t slot) {
 int collect_timing(ccsdt_ctx* ctx, StageBuf& b) {
   if(!b.timing_pending) return 0;
   CK(cudaEventSynchronize(b.done));
-  float ms = 0;
-  CK(cudaEventElapsedTime(&ms, b.k0, b.k1));
-  ctx->stats.seconds_kernel += ms * 1e-3;
+  // Consecutive tasks run on two compute streams, so the [k0,k1] intervals of neighbours overlap (a task's
+  // CTAs fill the SMs the previous task's tail frees): seconds_kernel is the length of the UNION of the
+  // intervals, accumulated in launch order on the time line of ev_base.
+  float ms = 0, ms0 = 0, ms1 = 0;
+  CK(cudaEventElapsedTime(&ms0, ctx->ev_base, b.k0));
+  CK(cudaEventElapsedTime(&ms1, ctx->ev_base, b.k1));
+  const double start = std::max((double) ms0, ctx->kernel_busy_until);
+  if(ms1 > start) ctx->stats.seconds_kernel += (ms1 - start) * 1e-3;
+  ctx->kernel_busy_until = std::max(ctx->kernel_busy_until, (double) ms1);
   CK(cudaEventElapsedTime(&ms, b.g0, b.g1));
   ctx->stats.seconds_staging += ms * 1e-3;
   b.timing_pending = false;
@@ -831,8 +842,13 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
       ctx->task_energy_cap = cap + 16;
       CK(cudaMalloc(&ctx->d_task_energy, (size_t) ctx->task_energy_cap * 16));
     }
-    CK(cudaMemsetAsync(ctx->d_error, 0, 4, ctx->s_compute));
     const int nbuf = ctx->opt.overlap ? 2 : 1;
+    ctx->buf[0].cs = ctx->s_compute;
+    ctx->buf[1].cs = ctx->opt.overlap ? ctx->s_compute2 : ctx->s_compute;
+    CK(cudaMemsetAsync(ctx->d_error, 0, 4, ctx->s_compute));
+    CK(cudaEventRecord(ctx->ev_base, ctx->s_compute));
+    CK(cudaStreamWaitEvent(ctx->s_compute2, ctx->ev_base, 0));
+    ctx->kernel_busy_until = 0.0;
     for(int64_t j = 0;; j++) {
       const int64_t ti = next_task();
       if(ti < 0) break;
@@ -850,9 +866,10 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
       ctx->stats.evaluated_flops += ops * (ctx->opt.kernel == CCSDT_KERNEL_DMMA ? b.eval_fraction : 1.0);
     }
     const int64_t n = (int64_t) mine.size();
-    for(int i = 0; i < nbuf; i++)
-      if(int rc = collect_timing(ctx, ctx->buf[i])) return rc;
+    for(int64_t k = std::max<int64_t>(0, n - nbuf); k < n; k++) // launch order (the interval union needs it)
+      if(int rc = collect_timing(ctx, ctx->buf[k % nbuf])) return rc;
     cudaError_t e = cudaStreamSynchronize(ctx->s_compute);
+    if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_compute2);
     if(e != cudaSuccess) {
       return ctx->fail(std::string("fused kernel failed: ") + cudaGetErrorName(e) + " " + cudaGetErrorString(e) +
                        " (a pipeline timeout traps instead of hanging)", 9);
@@ -945,6 +962,8 @@ int ccsdt_create(ccsdt_ctx** out, int device) {
      !ctx->encode_fn)
     return bail("cuTensorMapEncodeTiled not available from the driver");
   if((e = cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  if((e = cudaStreamCreateWithFlags(&ctx->s_compute2, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  if((e = cudaEventCreate(&ctx->ev_base)) != cudaSuccess) return bail(cudaGetErrorString(e));
   if((e = cudaStreamCreateWithFlags(&ctx->s_stage, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
   if((e = cudaMalloc(&ctx->d_error, 4)) != cudaSuccess) return bail(cudaGetErrorString(e));
   cudaMemset(ctx->d_error, 0, 4);
@@ -973,6 +992,8 @@ int ccsdt_destroy(ccsdt_ctx* ctx) {
     if(kv.second.dev) cudaFree(kv.second.dev);
   if(ctx->h_fetch) cudaFreeHost(ctx->h_fetch);
   if(ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+  if(ctx->s_compute2) cudaStreamDestroy(ctx->s_compute2);
+  if(ctx->ev_base) cudaEventDestroy(ctx->ev_base);
   if(ctx->s_stage) cudaStreamDestroy(ctx->s_stage);
   delete ctx;
   return 0;
