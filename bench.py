@@ -45,8 +45,8 @@ CPU_SAMPLE_TS = 14
 CPU_SAMPLE_TASKS = 3
 # dram__bytes_read.sum + dram__bytes_write.sum of one fused-kernel launch (ncu --set full, profiles/): the
 # N=1 workload's largest task, and the N>1 workload's task 5000
-NCU_TRAFFIC = {"benzene": {"bytes": 4.58e9, "task": "task 0 (21,21,21,40,40,40)", "report": "profiles/ncu_r01_benzene_task0.txt"},
-               "synth": {"bytes": 9.93e10, "task": "task 5000 (32,28,28,32,32,20)", "report": "profiles/ncu_r01_n60v500_task5000.txt"}}
+NCU_TRAFFIC = {"benzene": {"bytes": 5.87e8, "task": "task 0 (21,21,21,40,40,40), symmetry on: 9 975 of 166 375 boxes, 2.88 ms", "report": "profiles/ncu_r01_benzene_task0.txt"},
+               "synth": {"bytes": 9.79e10, "task": "task 5000 (32,28,28,32,32,20), no coinciding tiles", "report": "profiles/ncu_r01_n60v500_task5000.txt"}}
 
 
 def orbital_energies(w):

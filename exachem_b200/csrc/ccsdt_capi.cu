@@ -671,6 +671,7 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
       if(t.t[1] == t.t[2] && P.c[1] == P.c[2]) P.sym |= 2;
       if(t.t[3] == t.t[4]) P.sym |= 4;
       if(t.t[4] == t.t[5]) P.sym |= 8;
+      if((P.sym & 3) == 3 && P.c[0] == 2) P.sym |= 16;
     }
     if(P.sym) {
       std::array<int, 19> key;

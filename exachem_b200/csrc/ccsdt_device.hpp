@@ -92,14 +92,17 @@ struct alignas(64) TaskParams {
   // coincide, the summand d*d/D and d*(d+s)/D is symmetric under exchange of the two element indices
   // (t3 is antisymmetric in same-spin indices), so only boxes with ascending box coordinates along
   // coinciding indices are evaluated and their partials are weighted by the number of distinct
-  // permutations (1, 2, 3 or 6 per index family).  sym bits: 0 = h1~h2, 1 = h2~h3, 2 = p4~p5, 3 = p5~p6.
+  // permutations (1, 2, 3 or 6 per index family).  sym bits: 0 = h1~h2, 1 = h2~h3, 2 = p4~p5, 3 = p5~p6,
+  // 4 = hole boxes are 2 wide (see box_weight).
   // box_list (device, brick-major order of the surviving ids of the padded grid) replaces the id range.
   int32_t        sym;
   int32_t        nlist;
   const int32_t* box_list;
 };
 
-// weight of a box under the task's symmetry bits; 0 = the box is a mirror image and is skipped
+// weight of a box under the task's symmetry bits; 0 = the box is a mirror image and is skipped.
+// sym bit 4: the hole boxes are 2 wide, so a box on the triple diagonal of three coinciding hole tiles only
+// holds elements with a repeated hole index, where the antisymmetric t3 vanishes: skipped as well.
 __host__ __device__ inline int box_weight(int sym, const int bi[6]) {
   int w = 1;
   for(int f = 0; f < 2; f++) {
@@ -107,6 +110,7 @@ __host__ __device__ inline int box_weight(int sym, const int bi[6]) {
     const bool s01 = (sym >> (2 * f)) & 1, s12 = (sym >> (2 * f + 1)) & 1;
     if(s01 && a > b) return 0;
     if(s12 && b > c) return 0;
+    if(f == 0 && (sym & 16) && s01 && s12 && a == b && b == c) return 0;
     if(s01 && s12) w *= (a < b && b < c) ? 6 : ((a < b || b < c) ? 3 : 1);
     else if(s01) w *= a < b ? 2 : 1;
     else if(s12) w *= b < c ? 2 : 1;

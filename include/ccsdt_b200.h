@@ -122,7 +122,9 @@ CCSDT_API int     ccsdt_partition(int noab, int nvab, const int32_t* k_spin, con
 CCSDT_API int     ccsdt_check_memory(int tilesize, int nbf, size_t gpu_bytes, size_t* required);
 /* permutation weight the fused kernel gives CTA box `box` (box coordinates along h1,h2,h3,p4,p5,p6) under
  * symmetry bits `sym` (bit 0: tiles h1b==h2b, 1: h2b==h3b, 2: p4b==p5b, 3: p5b==p6b); 0 = the box is the
- * mirror image of an evaluated one and is skipped.  Summed over a tile's boxes the weights count every box once. */
+ * mirror image of an evaluated one and is skipped.  Summed over a tile's boxes the weights count every box once.
+ * Bit 4 (hole boxes are 2 wide, set together with bits 0 and 1) also skips the boxes on the triple hole diagonal:
+ * all their elements repeat a hole index, where t3 vanishes by antisymmetry. */
 CCSDT_API int     ccsdt_box_weight(int sym, const int32_t box[6]);
 
 /* problem definition */

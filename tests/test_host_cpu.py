@@ -115,3 +115,12 @@ def test_box_weights_count_every_box_once(sym):
     assert total == int(np.prod(n))
     if sym:
         assert kept < int(np.prod(n))
+
+
+def test_box_weight_skips_the_triple_hole_diagonal():
+    import ctypes as C
+    import itertools
+    L = _lib.load()
+    n = [5, 5, 5, 2, 3, 2]
+    total = sum(L.ccsdt_box_weight(3 | 16, (C.c_int32 * 6)(*b)) for b in itertools.product(*[range(k) for k in n]))
+    assert total == int(np.prod(n)) - 5 * 2 * 3 * 2       # the 5 diagonal hole boxes of every particle box are dropped

@@ -215,67 +215,102 @@ def pivoted_cholesky(eri_mo, diagtol):
 
 
 # ------------------------------------------------------------------------------------------------ CCSD
+class SpinOrbitalIntegrals:
+    """<pq||rs> over spin orbitals ordered | occ a | occ b | virt a | virt b |, built block by block from the
+    spatial (pq|rs) (the full spin-orbital tensor of benzene would be 21 GB)."""
+
+    def __init__(self, eps, eri_mo, nocc):
+        n = len(eps)
+        nvir = n - nocc
+        self.eri = eri_mo
+        self.spat = np.concatenate([np.arange(nocc), np.arange(nocc), np.arange(nocc, n), np.arange(nocc, n)])
+        self.spin = np.concatenate([np.zeros(nocc, int), np.ones(nocc, int), np.zeros(nvir, int), np.ones(nvir, int)])
+        self.eso = eps[self.spat]
+        self.no = 2 * nocc
+        self.rng = {"o": np.arange(0, 2 * nocc), "v": np.arange(2 * nocc, 2 * n)}
+
+    def block(self, kinds):
+        """kinds e.g. "oovv" -> <ij||ab>"""
+        P, Q, R, S = (self.rng[k] for k in kinds)
+        sp, sn = self.spat, self.spin
+        d = lambda a, b: (sn[a][:, None] == sn[b][None, :]).astype(float)  # noqa: E731
+        # <pq|rs> = (pr|qs)
+        out = self.eri[np.ix_(sp[P], sp[R], sp[Q], sp[S])].transpose(0, 2, 1, 3) * d(P, R)[:, None, :, None] * d(Q, S)[None, :, None, :]
+        out = np.ascontiguousarray(out)
+        x = self.eri[np.ix_(sp[P], sp[S], sp[Q], sp[R])].transpose(0, 2, 3, 1) * d(P, S)[:, None, None, :] * d(Q, R)[None, :, :, None]
+        out -= x
+        return out
+
+
 def spin_orbital_integrals(eps, eri_mo, nocc):
-    """<pq||rs> over spin orbitals ordered | occ a | occ b | virt a | virt b | from spatial (pq|rs)."""
-    n = len(eps)
-    nvir = n - nocc
-    spat = np.concatenate([np.arange(nocc), np.arange(nocc), np.arange(nocc, n), np.arange(nocc, n)])
-    spin = np.concatenate([np.zeros(nocc, int), np.ones(nocc, int), np.zeros(nvir, int), np.ones(nvir, int)])
-    g = eri_mo[np.ix_(spat, spat, spat, spat)]                        # (pq|rs) chemists, spatial parts
-    same = (spin[:, None] == spin[None, :]).astype(float)
-    g = g * same[:, :, None, None] * same[None, None, :, :]
-    phys = g.transpose(0, 2, 1, 3)                                    # <pr|qs> = (pq|rs)
-    anti = phys - phys.transpose(0, 1, 3, 2)
-    return anti, eps[spat], spin
+    """full <pq||rs> tensor (small molecules only), orbital energies and spins"""
+    so = SpinOrbitalIntegrals(eps, eri_mo, nocc)
+    allr = np.arange(len(so.spat))
+    so.rng = {"o": allr, "v": allr}
+    return so.block("oooo"), so.eso, so.spin
 
 
-def ccsd(anti, eso, no, conv=1e-11, maxiter=200, ndiis=8):
-    """Stanton et al. spin-orbital CCSD (canonical RHF orbitals: f is diagonal).  no = occupied spin orbitals.
-    Returns E_corr, t1[i,a], t2[i,j,a,b], iterations."""
-    o, v = slice(0, no), slice(no, None)
+def ccsd(ints, eso=None, no=None, conv=1e-11, maxiter=200, ndiis=8, verbose=False):
+    """Stanton et al. spin-orbital CCSD (canonical RHF orbitals: f is diagonal).  `ints` is a SpinOrbitalIntegrals
+    (or, with eso and no, a full <pq||rs> array).  W_abef is never stored: its three pieces are contracted with
+    tau directly.  Returns E_corr, t1[i,a], t2[i,j,a,b], iterations."""
+    es = lambda *a: np.einsum(*a, optimize=True)  # noqa: E731
+    if isinstance(ints, SpinOrbitalIntegrals):
+        eso, no = ints.eso, ints.no
+        blk = ints.block
+    else:
+        o_, v_ = slice(0, no), slice(no, None)
+        sl = {"o": o_, "v": v_}
+        blk = lambda k: ints[sl[k[0]], sl[k[1]], sl[k[2]], sl[k[3]]]  # noqa: E731
     nv = len(eso) - no
-    fo, fv = eso[o], eso[v]
+    fo, fv = eso[:no], eso[no:]
     Dia = fo[:, None] - fv[None, :]
     Dijab = fo[:, None, None, None] + fo[None, :, None, None] - fv[None, None, :, None] - fv[None, None, None, :]
-    oovv, ooov, ovvv = anti[o, o, v, v], anti[o, o, o, v], anti[o, v, v, v]
-    oooo, vvvv, ovvo, ovov = anti[o, o, o, o], anti[v, v, v, v], anti[o, v, v, o], anti[o, v, o, v]
-    vvvo, ovoo = anti[v, v, v, o], anti[o, v, o, o]
+    oovv, ooov, ovvv = blk("oovv"), blk("ooov"), blk("ovvv")
+    oooo, vvvv, ovvo, ovov = blk("oooo"), blk("vvvv"), blk("ovvo"), blk("ovov")
+    vvvv2 = vvvv.reshape(nv * nv, nv * nv)
     t1 = np.zeros((no, nv))
     t2 = oovv / Dijab
     E = 0.25 * np.sum(oovv * t2)
     hist_t, hist_e = [], []
     for it in range(maxiter):
-        tt = np.einsum("ia,jb->ijab", t1, t1)
+        tt = es("ia,jb->ijab", t1, t1)
         ttau = t2 + 0.5 * (tt - tt.transpose(0, 1, 3, 2))
         tau = t2 + tt - tt.transpose(0, 1, 3, 2)
-        Fae = (np.einsum("mf,mafe->ae", t1, ovvv) - 0.5 * np.einsum("mnaf,mnef->ae", ttau, oovv))
-        Fmi = (np.einsum("ne,mnie->mi", t1, ooov) + 0.5 * np.einsum("inef,mnef->mi", ttau, oovv))
-        Fme = np.einsum("nf,mnef->me", t1, oovv)
-        Wmnij = oooo + np.einsum("je,mnie->mnij", t1, ooov) - np.einsum("ie,mnje->mnij", t1, ooov) \
-            + 0.25 * np.einsum("ijef,mnef->mnij", tau, oovv)
-        # <am||ef> = -<ma||ef>
-        Wabef = vvvv + np.einsum("mb,maef->abef", t1, ovvv) - np.einsum("ma,mbef->abef", t1, ovvv) \
-            + 0.25 * np.einsum("mnab,mnef->abef", tau, oovv)
+        del tt
+        Fae = es("mf,mafe->ae", t1, ovvv) - 0.5 * es("mnaf,mnef->ae", ttau, oovv)
+        Fmi = es("ne,mnie->mi", t1, ooov) + 0.5 * es("inef,mnef->mi", ttau, oovv)
+        Fme = es("nf,mnef->me", t1, oovv)
+        Wmnij = oooo + es("je,mnie->mnij", t1, ooov) - es("ie,mnje->mnij", t1, ooov) + 0.25 * es("ijef,mnef->mnij", tau, oovv)
         # <mn||ej> = -<mn||je>
-        Wmbej = ovvo + np.einsum("jf,mbef->mbej", t1, ovvv) + np.einsum("nb,mnje->mbej", t1, ooov) \
-            - np.einsum("jnfb,mnef->mbej", 0.5 * t2 + np.einsum("jf,nb->jnfb", t1, t1), oovv)
+        Wmbej = ovvo + es("jf,mbef->mbej", t1, ovvv) + es("nb,mnje->mbej", t1, ooov) \
+            - es("jnfb,mnef->mbej", 0.5 * t2 + es("jf,nb->jnfb", t1, t1), oovv)
         # T1
-        r1 = (np.einsum("ie,ae->ia", t1, Fae) - np.einsum("ma,mi->ia", t1, Fmi) + np.einsum("imae,me->ia", t2, Fme)
-              - np.einsum("nf,naif->ia", t1, ovov) - 0.5 * np.einsum("imef,maef->ia", t2, ovvv)
-              - 0.5 * np.einsum("mnae,nmei->ia", t2, -ooov.transpose(0, 1, 3, 2)))
+        r1 = (es("ie,ae->ia", t1, Fae) - es("ma,mi->ia", t1, Fmi) + es("imae,me->ia", t2, Fme)
+              - es("nf,naif->ia", t1, ovov) - 0.5 * es("imef,maef->ia", t2, ovvv)
+              + 0.5 * es("mnae,nmie->ia", t2, ooov))          # -1/2 t_mn^ae <nm||ei>, <nm||ei> = -<nm||ie>
         # T2
-        Fbe = Fae - 0.5 * np.einsum("mb,me->be", t1, Fme)
-        Fmj = Fmi + 0.5 * np.einsum("je,me->mj", t1, Fme)
-        x = np.einsum("ijae,be->ijab", t2, Fbe)
+        Fbe = Fae - 0.5 * es("mb,me->be", t1, Fme)
+        Fmj = Fmi + 0.5 * es("je,me->mj", t1, Fme)
+        x = es("ijae,be->ijab", t2, Fbe)
         r2 = oovv + x - x.transpose(0, 1, 3, 2)
-        x = np.einsum("imab,mj->ijab", t2, Fmj)
+        x = es("imab,mj->ijab", t2, Fmj)
         r2 -= x - x.transpose(1, 0, 2, 3)
-        r2 += 0.5 * np.einsum("mnab,mnij->ijab", tau, Wmnij) + 0.5 * np.einsum("ijef,abef->ijab", tau, Wabef)
-        x = np.einsum("imae,mbej->ijab", t2, Wmbej) - np.einsum("ie,ma,mbej->ijab", t1, t1, ovvo)
+        r2 += 0.5 * es("mnab,mnij->ijab", tau, Wmnij)
+        # 1/2 tau_ij^ef W_abef with W_abef = <ab||ef> + P(ab) t_m^b <ma||ef> + 1/4 tau_mn^ab <mn||ef>
+        r2 += 0.5 * (tau.reshape(no * no, nv * nv) @ vvvv2.T).reshape(no, no, nv, nv)
+        y = es("ijef,maef->ijma", tau, ovvv)                       # sum_ef tau_ij^ef <ma||ef>
+        x = es("mb,ijma->ijab", t1, y)
+        r2 += 0.5 * (x - x.transpose(0, 1, 3, 2))
+        y = es("ijef,mnef->ijmn", tau, oovv)
+        r2 += 0.125 * es("mnab,ijmn->ijab", tau, y)
+        x = es("imae,mbej->ijab", t2, Wmbej) - es("ie,ma,mbej->ijab", t1, t1, ovvo)
         r2 += x - x.transpose(1, 0, 2, 3) - x.transpose(0, 1, 3, 2) + x.transpose(1, 0, 3, 2)
-        x = np.einsum("ie,abej->ijab", t1, vvvo)
+        # P(ij) t_i^e <ab||ej>, <ab||ej> = <ej||ab> = -<je||ab>... use ovvv: <ab||ej> = <ej||ab> = -<je||ab> = <je||ba>
+        x = es("ie,jeba->ijab", t1, ovvv)
         r2 += x - x.transpose(1, 0, 2, 3)
-        x = np.einsum("ma,mbij->ijab", t1, ovoo)
+        # -P(ab) t_m^a <mb||ij>, <mb||ij> = <ij||mb> = ooov[i,j,m,b]
+        x = es("ma,ijmb->ijab", t1, ooov)
         r2 -= x - x.transpose(0, 1, 3, 2)
         n1, n2 = r1 / Dia, r2 / Dijab
         res = np.sqrt(np.sum((n1 - t1) ** 2) + np.sum((n2 - t2) ** 2))
@@ -292,7 +327,9 @@ def ccsd(anti, eso, no, conv=1e-11, maxiter=200, ndiis=8):
             c = np.linalg.solve(B, rhs)[:m]
             vec = sum(ci * ti for ci, ti in zip(c, hist_t))
         t1, t2 = vec[:no * nv].reshape(no, nv), vec[no * nv:].reshape(no, no, nv, nv)
-        Enew = 0.25 * np.sum(oovv * t2) + 0.5 * np.einsum("ijab,ia,jb->", oovv, t1, t1)
+        Enew = 0.25 * np.sum(oovv * t2) + 0.5 * es("ijab,ia,jb->", oovv, t1, t1)
+        if verbose:
+            print(f"  ccsd iter {it + 1}: E = {Enew:.12f}  residual {res:.3e}", flush=True)
         if res < conv and abs(Enew - E) < conv:
             E = Enew
             break
@@ -354,8 +391,7 @@ def solve(input_json, basis_dir, diagtol=None, verbose=True):
     ncv = None
     if diagtol:
         eri_mo, ncv = pivoted_cholesky(eri_mo, diagtol)
-    anti, eso, _ = spin_orbital_integrals(eps, eri_mo, no)
-    ecc, t1, t2, it_cc = ccsd(anti, eso, 2 * no)
+    ecc, t1, t2, it_cc = ccsd(SpinOrbitalIntegrals(eps, eri_mo, no), verbose=verbose)
     info = dict(nbf=int(len(eps)), nocc=int(no), e_nuc=float(mol.nuclear_repulsion()), e_scf=float(escf),
                 e_ccsd_corr=float(ecc), scf_iterations=int(it_scf), ccsd_iterations=int(it_cc), cholesky_vectors=ncv)
     if verbose:
