@@ -716,7 +716,7 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     P.stagger_cycles = (ctas > 1 && ctx->opt.stagger && nboxes >= 4 * in_flight)
                          ? (int) std::min<int64_t>(ksteps * 256 + 8192, 50000000)
                          : 0;
-    need_partial    = padded;
+    need_partial    = P.box_list ? std::max<int64_t>(P.nlist, 1) : padded; // one partial per evaluated box
   }
   b.nparts = need_partial;
   if(need_partial > b.partial_cap) {

@@ -74,7 +74,8 @@ struct alignas(64) TaskParams {
   int32_t     ns1;
   S1Dev       s1[9];
   const double* evl[6]; // orbital-energy slices of the six tiles
-  double*     partial;  // [nboxes_padded][2] per-box energy partials (zero for ids that are not boxes)
+  double*     partial;  // [nboxes_padded][2] per-box energy partials (zero for ids that are not boxes);
+                        // [nlist][2] in list order for a symmetry-reduced task
   int32_t     nboxes;   // boxes of the tile
   // Box ids are handed out in brick-major order: a brick is a (brick[0..5])-shaped group of boxes that
   // is as close to a 6-d cube (in elements) as the tile allows, so that the boxes in flight at any

@@ -338,6 +338,7 @@ __device__ __forceinline__ void produce_term(const TaskParams& p, const TermDev&
 constexpr int BOXQ = MAX_STAGES + 2;
 struct BoxQueueEntry {
   int      id;
+  int      slot; // index of the box's partial: the id, or the position in the symmetry-reduced list
   BoxCoord bc;
 };
 
@@ -390,11 +391,11 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
     }
     __syncwarp();
     for(int seq = 0;; seq++) {
-      int      id = -1;
+      int      id = -1, slot = 0;
       BoxCoord bc;
       if(lane == 0) {
         for(;;) {
-          id = (int) atomicAdd(p.box_counter, 1u);
+          id = slot = (int) atomicAdd(p.box_counter, 1u);
           if(p.box_list) { // symmetry-reduced task: dense list of the surviving ids
             id = id < p.nlist ? __ldg(p.box_list + id) : -1;
             if(id >= 0) decode_box(p, id, bc);
@@ -408,6 +409,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
         }
         BoxQueueEntry& e = boxq[seq % BOXQ];
         e.id             = id;
+        e.slot           = slot;
         e.bc             = bc;
         if(id < 0) {
           // end marker: complete one more phase of the next full barrier without data
@@ -573,9 +575,10 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
     if(tid == 0) {
       double a = 0.0, b = 0.0;
       for(int i = 0; i < ncw; i++) a += red[0][i], b += red[1][i];
-      const double w = (double) boxq[seq % BOXQ].bc.weight; // the entry outlives the box (see BOXQ)
-      p.partial[2 * (int64_t) box]     = w * a;
-      p.partial[2 * (int64_t) box + 1] = w * b;
+      const BoxQueueEntry& e = boxq[seq % BOXQ]; // the entry outlives the box (see BOXQ)
+      const double         w = (double) e.bc.weight;
+      p.partial[2 * (int64_t) e.slot]     = w * a;
+      p.partial[2 * (int64_t) e.slot + 1] = w * b;
     }
     named_bar_sync(1, ncw * 32); // red[] may be overwritten by the next box
   }
