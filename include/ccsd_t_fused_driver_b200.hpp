@@ -26,6 +26,7 @@
 #include "ccsdt_b200.h"
 
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -141,6 +142,8 @@ std::tuple<T, T, double, double> CCSD_T_Fused_Driver<T>::execute(
   ccsdt_default_options(&opt);
   opt.rank   = (int32_t) ec.pg().rank().value();
   opt.nranks = (int32_t) ec.pg().size().value();
+  // CCSDT_B200_SYMMETRY=0 evaluates every element of every task as the reference does (see ccsdt_options.symmetry)
+  if(const char* e = std::getenv("CCSDT_B200_SYMMETRY")) opt.symmetry = std::atoi(e) != 0;
   check(ccsdt_set_options(ctx, &opt));
   check(ccsdt_set_space(ctx, s.noa, s.nob, s.nva, s.nvb, s.k_range.data(), s.k_spin.data(), evl.data(),
                         is_restricted ? 1 : 0));
