@@ -641,6 +641,9 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     b.smem           = (size_t) stages * P.stage_bytes + 1024;
     b.consumer_warps = ncw;
     const int64_t in_flight = (int64_t) ctx->prop.multiProcessorCount * ctas;
+    // (A staging block cannot start on an SM that holds three fused CTAs: the register file is partitioned per
+    // scheduler and three of the four partitions are full -- tools/probes/coresidency.cu.  Leaving CTA slots free
+    // for the panel build was measured: it hides the build but costs the same time in the fused kernel.)
     b.grid           = (int) std::min<int64_t>(nboxes, in_flight);
     // bricks: grow the index with the smallest element extent until one brick holds about as many
     // boxes as there are CTAs in flight, then even the bricks out over each index
@@ -738,11 +741,14 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     sp.spin_range(true, 1, tb, te, n);  si.nva = (int) n;
     sp.spin_range(true, 2, tb, te, n);  si.nvb = (int) n;
   }
+  // the buffer's partials and box-scheduler words are zeroed here, on the staging stream, long before the launch
+  // (ids of the padded brick grid that are not boxes are never written: their partials stay zero)
+  CK(launch_zero(b.d_partial, 2 * b.nparts, b.d_counter, COUNTER_WORDS, ctx->s_stage));
   CK(cudaEventRecord(b.g0, ctx->s_stage));
   CK(launch_gather(b.d_descs, nd, max_elems, si, ctx->s_stage));
   CK(cudaEventRecord(b.g1, ctx->s_stage));
   CK(cudaEventRecord(b.staged, ctx->s_stage));
-  ctx->stats.kernel_launches += (nd + 65534) / 65535;
+  ctx->stats.kernel_launches += 1 + (nd + 65534) / 65535;
   return 0;
 }
 
@@ -756,14 +762,10 @@ int launch_task(ccsdt_ctx* ctx, StageBuf& b, int64_t slot) {
   }
   else if(b.params.nterms == 0) {
     // no doubles contraction is enabled: d = 0 for every element, so E[T] and E(T) of the task are exactly 0
-    CK(cudaEventRecord(b.k0, b.cs));
-    CK(cudaMemsetAsync(b.d_partial, 0, (size_t) b.nparts * 16, b.cs));
+    CK(cudaEventRecord(b.k0, b.cs)); // the staging stream zeroed the partials
     CK(cudaEventRecord(b.k1, b.cs));
   }
   else {
-    // ids of the padded brick grid that are not boxes are never written: their partials stay zero
-    CK(cudaMemsetAsync(b.d_partial, 0, (size_t) b.nparts * 16, b.cs));
-    CK(cudaMemsetAsync(b.d_counter, 0, 4 * COUNTER_WORDS, b.cs));
     CK(cudaEventRecord(b.k0, b.cs));
     CK(launch_fused_dmma(b.params, b.grid, b.consumer_warps, b.smem, b.cs));
     CK(cudaEventRecord(b.k1, b.cs));
@@ -965,7 +967,12 @@ int ccsdt_create(ccsdt_ctx** out, int device) {
   if((e = cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
   if((e = cudaStreamCreateWithFlags(&ctx->s_compute2, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
   if((e = cudaEventCreate(&ctx->ev_base)) != cudaSuccess) return bail(cudaGetErrorString(e));
-  if((e = cudaStreamCreateWithFlags(&ctx->s_stage, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  {
+    // staging blocks (128 threads x 32 registers) slot in next to the resident fused CTAs; give them priority
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if((e = cudaStreamCreateWithPriority(&ctx->s_stage, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  }
   if((e = cudaMalloc(&ctx->d_error, 4)) != cudaSuccess) return bail(cudaGetErrorString(e));
   cudaMemset(ctx->d_error, 0, 4);
   if((e = fused_dmma_configure((size_t) ctx->prop.sharedMemPerBlockOptin - 2048)) != cudaSuccess)

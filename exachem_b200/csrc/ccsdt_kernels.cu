@@ -22,8 +22,11 @@ namespace ccsdt {
 // =================================================================================================
 // panel build
 // =================================================================================================
-__global__ void __launch_bounds__(256) gather_panels_kernel(const GatherDesc* __restrict__ descs,
-                                                            SynthInfo si) {
+// Small blocks (128 threads x 32 registers) for the staging kernels: they slot into whatever an SM has free
+// while the fused kernel of the previous task drains (they cannot join an SM that holds three fused CTAs,
+// tools/probes/coresidency.cu).
+__global__ void __launch_bounds__(128, 16) gather_panels_kernel(const GatherDesc* __restrict__ descs,
+                                                                SynthInfo si) {
   const GatherDesc& d  = descs[blockIdx.y];
   const int64_t     n3 = d.n[3], n2 = d.n[2], n1 = d.n[1];
   const int64_t     total = (int64_t) d.n[0] * n1 * n2 * n3;
@@ -52,13 +55,30 @@ __global__ void __launch_bounds__(256) gather_panels_kernel(const GatherDesc* __
 cudaError_t launch_gather(const GatherDesc* dev_descs, int ndesc, int64_t max_elems, SynthInfo si,
                           cudaStream_t st) {
   if(ndesc <= 0) return cudaSuccess;
-  int64_t bx = (max_elems + 256 * 8 - 1) / (256 * 8);
+  int64_t bx = (max_elems + 128 * 8 - 1) / (128 * 8);
   if(bx < 1) bx = 1;
-  if(bx > 1024) bx = 1024;
+  if(bx > 2048) bx = 2048;
   for(int off = 0; off < ndesc; off += 65535) {
     const int n = ndesc - off < 65535 ? ndesc - off : 65535;
-    gather_panels_kernel<<<dim3((unsigned) bx, (unsigned) n), 256, 0, st>>>(dev_descs + off, si);
+    gather_panels_kernel<<<dim3((unsigned) bx, (unsigned) n), 128, 0, st>>>(dev_descs + off, si);
   }
+  return cudaGetLastError();
+}
+
+// zeroes the per-box partials and the box-scheduler words of a staging buffer (instead of two cudaMemsetAsync,
+// whose kernels need not fit next to the resident fused CTAs)
+__global__ void __launch_bounds__(128, 16) zero_words_kernel(double* __restrict__ a, int64_t na, uint32_t* __restrict__ b,
+                                                             int nb) {
+  const int64_t i0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t) gridDim.x * blockDim.x;
+  for(int64_t i = i0; i < na; i += stride) a[i] = 0.0;
+  for(int64_t i = i0; i < nb; i += stride) b[i] = 0u;
+}
+
+cudaError_t launch_zero(double* a, int64_t na, uint32_t* b, int nb, cudaStream_t st) {
+  int64_t blocks = (na + 128 * 4 - 1) / (128 * 4);
+  if(blocks < 1) blocks = 1;
+  if(blocks > 592) blocks = 592;
+  zero_words_kernel<<<(unsigned) blocks, 128, 0, st>>>(a, na, b, nb);
   return cudaGetLastError();
 }
 
@@ -586,8 +606,19 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
 
 // <160,3>: 4+1 warps, three CTAs per SM at 128 registers; <288,1>: 8+1 warps, one CTA per SM with up to
 // 224 registers (no spills); <416,1>: 12+1 warps, one CTA per SM at 152 registers.
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out2);
+
 cudaError_t fused_dmma_configure(size_t smem_bytes) {
   cudaError_t e;
+  // Every kernel of a run asks for the same L1/shared-memory split (all shared): CTAs of kernels that prefer
+  // different carve-outs cannot share an SM, and the staging kernels are meant to run next to the fused CTAs.
+  const int carve = (int) cudaSharedmemCarveoutMaxShared;
+  if((e = cudaFuncSetAttribute(gather_panels_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
+  if((e = cudaFuncSetAttribute(zero_words_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
+  if((e = cudaFuncSetAttribute(reduce_partials_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
+  if((e = cudaFuncSetAttribute(fused_t_dmma_kernel<160, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
+  if((e = cudaFuncSetAttribute(fused_t_dmma_kernel<288, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
+  if((e = cudaFuncSetAttribute(fused_t_dmma_kernel<416, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
   if((e = cudaFuncSetAttribute(fused_t_dmma_kernel<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int) smem_bytes)) != cudaSuccess)
     return e;
@@ -620,18 +651,18 @@ cudaError_t launch_fused_dmma(const TaskParams& p, int grid, int consumer_warps,
 // =================================================================================================
 // fixed-order reduction of per-box partials: out2[0..1] = sum(partial[:,0]), sum(partial[:,1])
 // =================================================================================================
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partial, int n,
-                                                              double* __restrict__ out2) {
-  __shared__ double sh[2][256];
+__global__ void __launch_bounds__(128, 16) reduce_partials_kernel(const double* __restrict__ partial, int n,
+                                                                  double* __restrict__ out2) {
+  __shared__ double sh[2][128];
   double            a = 0.0, b = 0.0;
-  for(int i = threadIdx.x; i < n; i += 256) {
+  for(int i = threadIdx.x; i < n; i += 128) {
     a += partial[2 * (int64_t) i];
     b += partial[2 * (int64_t) i + 1];
   }
   sh[0][threadIdx.x] = a;
   sh[1][threadIdx.x] = b;
   __syncthreads();
-  for(int s = 128; s > 0; s >>= 1) {
+  for(int s = 64; s > 0; s >>= 1) {
     if((int) threadIdx.x < s) {
       sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
       sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
@@ -642,7 +673,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
 }
 
 cudaError_t launch_reduce_partials(const double* partial, int n, double* out2, cudaStream_t st) {
-  reduce_partials_kernel<<<1, 256, 0, st>>>(partial, n, out2);
+  reduce_partials_kernel<<<1, 128, 0, st>>>(partial, n, out2);
   return cudaGetLastError();
 }
 
