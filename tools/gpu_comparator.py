@@ -113,6 +113,8 @@ def main():
         run_shape("small parity case (O=4,V=10 per spin, tile 6), whole job", 4, 10, 6, -1, kinds),
         run_shape("benzene cc-pVDZ shape (O=21,V=93 per spin, tile 40), whole job", 21, 93, 40, -1, kinds),
         run_shape(f"synthetic (60,500) tile 32, first {args.big_tasks} kernel tasks", 60, 500, 32, args.big_tasks, kinds),
+        # BASELINE configs[2]: caffeine cc-pVDZ (O=51, V=195 per spin, ccsdt_tilesize 28 -> tiles 28,23 | 28x6,27)
+        run_shape("caffeine cc-pVDZ shape (O=51,V=195 per spin, tile 28), first 6 kernel tasks", 51, 195, 28, 6, kinds),
     ]
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
