@@ -48,6 +48,7 @@ SIGNATURES = {
     "ccsdt_put_block": (C.c_int, [C.c_void_p, C.c_int, _u32p, _dp]),
     "ccsdt_set_fetch": (C.c_int, [C.c_void_p, FETCH_FN, C.c_void_p]),
     "ccsdt_set_synthetic": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "ccsdt_put_cholesky": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "ccsdt_set_task_counter": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ccsdt_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _dp, C.POINTER(Stats)]),
     "ccsdt_run_tasks": (C.c_int, [C.c_void_p, _i64p, C.c_int64, _dp, _dp, C.POINTER(Stats)]),

@@ -201,6 +201,12 @@ class Context:
         self._keep.append(cb)
         self._ck(self.L.ccsdt_set_fetch(self.h, cb, None))
 
+    def put_cholesky(self, chol):
+        """setupV2Tensors on the device: chol[N, N, ncv] over all spin orbitals in tile order (cholVpr)."""
+        a = np.ascontiguousarray(chol, np.float64)
+        assert a.ndim == 3 and a.shape[0] == a.shape[1]
+        self._ck(self.L.ccsdt_put_cholesky(self.h, _p(a, _lib._dp), a.shape[2]))
+
     def set_synthetic(self, seed: int):
         self._ck(self.L.ccsdt_set_synthetic(self.h, seed))
 

@@ -19,6 +19,8 @@
  *                           ccsd_t_all_fused_singles.hpp:200,304; ..._doubles1.hpp:222,237,282;
  *                           ..._doubles2.hpp:215,230,335  (and the six LRUCache arguments: the HBM block
  *                           store replaces them)
+ *   ccsdt_put_cholesky   <- setupV2Tensors (the caller's step before execute)  exachem/cholesky/v2tensors.cpp:52-90,
+ *                           exachem/cc/ccsd_t/ccsd_t.cpp:168-193
  *   ccsdt_run / ccsdt_run_tasks <- execute's task loop + ccsd_t_fully_fused_none_df_none_task
  *                           ccsd_t_all_fused.hpp:77-286 + the kernel launcher ccsd_t_all_fused_gpu.cu:2571
  *                           + hostEnergyReduce ccsd_t_all_fused.hpp:19-32; returns the rank-partial
@@ -136,6 +138,11 @@ CCSDT_API int ccsdt_put_dense(ccsdt_ctx* ctx, int tensor, const double* host_den
 CCSDT_API int ccsdt_put_block(ccsdt_ctx* ctx, int tensor, const uint32_t bid[4], const double* host_block);
 CCSDT_API int ccsdt_set_fetch(ccsdt_ctx* ctx, ccsdt_fetch_fn fn, void* user);
 CCSDT_API int ccsdt_set_synthetic(ccsdt_ctx* ctx, uint64_t seed); /* procedural tensors generated on the device */
+/* The three V2 tensors formed on the device from Cholesky vectors: host_chol[N][N][ncv] over all spin orbitals in tile
+ * order (occupied first), what ExaChem holds as cholVpr.  Replaces setupV2Tensors (exachem/cholesky/v2tensors.cpp:52-90,
+ * called at exachem/cc/ccsd_t/ccsd_t.cpp:168-193): one cuBLAS DGEMM over the Cholesky index per tensor (libcublas is
+ * loaded on first use) plus an antisymmetrising gather.  Equivalent to ccsdt_put_dense on v2ijab, v2ijka and v2iabc. */
+CCSDT_API int ccsdt_put_cholesky(ccsdt_ctx* ctx, const double* host_chol, int64_t ncv);
 
 /* Dynamic task hand-out across ranks: `counter` points to an int64 in memory shared by all ranks of the
  * node (POSIX/SysV shared memory, an MPI shared window, ...), zeroed before every ccsdt_run by one rank

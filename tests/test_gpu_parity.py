@@ -371,3 +371,45 @@ def test_symmetry_reduction_headline_shape():
     assert np.allclose(res[1][3], res[0][3], rtol=1e-11, atol=0)
     assert res[1][2]["evaluated_flops"] < 0.35 * res[0][2]["evaluated_flops"]
     assert res[1][2]["seconds_kernel"] < 0.5 * res[0][2]["seconds_kernel"]
+
+
+def _spin_orbital_cholesky(oa, ob, va, vb, ncv, seed):
+    """random Cholesky-like vectors L[p,q,c] = L[q,p,c] over spin orbitals | occ a | occ b | virt a | virt b |, zero
+    between different spins (what ExaChem's cholVpr looks like), and the V2 tensors setupV2Tensors derives from them"""
+    rng = np.random.default_rng(seed)
+    spin = np.array([0] * oa + [1] * ob + [0] * va + [1] * vb)
+    n = len(spin)
+    L = rng.uniform(-1, 1, (n, n, ncv)) * 0.3
+    L = 0.5 * (L + L.transpose(1, 0, 2)) * (spin[:, None] == spin[None, :])[:, :, None]
+    O = oa + ob
+    Loo, Lov, Lvv = L[:O, :O], L[:O, O:], L[O:, O:]
+    v2ijab = np.einsum("iac,jbc->ijab", Lov, Lov) - np.einsum("ibc,jac->ijab", Lov, Lov)     # v2tensors.cpp:68-69
+    v2ijka = np.einsum("ikc,jac->ijka", Loo, Lov) - np.einsum("jkc,iac->ijka", Loo, Lov)     # v2tensors.cpp:77-78
+    v2iabc = np.einsum("ibc,adc->iabd", Lov, Lvv) - np.einsum("idc,abc->iabd", Lov, Lvv)     # v2tensors.cpp:85-86
+    return L, v2ijab, v2ijka, v2iabc
+
+
+@pytest.mark.parametrize("cfg", [(4, 4, 7, 7, 3, 13, 1), (5, 3, 9, 6, 4, 20, 2)])
+def test_v2_tensors_from_cholesky_vectors_on_the_device(orc, cfg):
+    """ccsdt_put_cholesky (row f2: setupV2Tensors on the GPU) must give the energies of the same V2 tensors built on
+    the host with the reference's formulas and uploaded with ccsdt_put_dense, and the oracle's"""
+    oa, ob, va, vb, ts, ncv, seed = cfg
+    restricted = oa == ob
+    sp, osp = drv.setup_mo_space(oa, ob, va, vb, ts), orc.tiles(oa, ob, va, vb, ts)
+    T = syn.dense_all(syn.Orbitals(oa, ob, va, vb), seed)
+    L, T["v2ijab"], T["v2ijka"], T["v2iabc"] = _spin_orbital_cholesky(oa, ob, va, vb, ncv, seed)
+    ref = orc.run(osp, T, restricted, per_task=True)
+    dense = run_gpu(sp, T, restricted)
+    ctx = drv.Context(0)
+    try:
+        ctx.set_space(sp, T["evl"], restricted)
+        ctx.put_dense(drv.T1, T["t1"])
+        ctx.put_dense(drv.T2, T["t2"])
+        ctx.put_cholesky(L)
+        n = len(drv.enumerate_tasks(sp, restricted)[0])
+        e1, e2, st, pt = ctx.run(per_task_n=n)
+    finally:
+        ctx.close()
+    assert _close(e1, ref[0]) and _close(e2, ref[1])
+    assert np.allclose(pt, ref[2], rtol=1e-11, atol=ATOL)
+    assert np.allclose(pt, dense[3], rtol=1e-12, atol=1e-12)
