@@ -979,6 +979,15 @@ int ccsdt_create(ccsdt_ctx** out, int device) {
   cudaMemset(ctx->d_error, 0, 4);
   if((e = fused_dmma_configure((size_t) ctx->prop.sharedMemPerBlockOptin - 2048)) != cudaSuccess)
     return bail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+  {
+    // fetched blocks come from the stream-ordered allocator: keep its memory across synchronisations (the default
+    // pool hands everything back to the driver at every sync, and each block upload is followed by one)
+    cudaMemPool_t pool = nullptr;
+    if(cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   ctx->block_budget = total_b / 2;

@@ -29,6 +29,7 @@
 #include <cstdlib>
 #include <string>
 #include <tuple>
+#include <type_traits>
 #include <vector>
 
 #ifndef CCSDT_B200_TERMINATE
@@ -53,6 +54,14 @@ int fetch_block(void* user, int tensor, const uint32_t bid[4], double* dst, size
   const int   nd = tensor == CCSDT_T1 ? 2 : 4;
   IndexVector id(nd);
   for(int i = 0; i < nd; i++) id[i] = (Index) bid[i];
+#if defined(CCSDT_B200_SPAN_TYPE)
+  // Tensor<T>::get of this TAMM takes a span: the block is written straight into the library's pinned buffer
+  // (define CCSDT_B200_SPAN_TYPE, e.g. to tamm::span, before including this header; T must be double)
+  if constexpr(std::is_same<T, double>::value) {
+    u->tensor[tensor]->get(id, CCSDT_B200_SPAN_TYPE<T>(dst, n));
+    return 0;
+  }
+#endif
   if(u->buf.size() < n) u->buf.resize(n);
   u->tensor[tensor]->get(id, u->buf);
   for(size_t i = 0; i < n; i++) dst[i] = (double) u->buf[i];

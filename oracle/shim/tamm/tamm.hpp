@@ -10,6 +10,7 @@
 // floating-point arithmetic stays in the reference sources.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <chrono>
 #include <cmath>
@@ -54,6 +55,19 @@ private:
   std::chrono::high_resolution_clock::time_point t0_;
 };
 
+// minimal span (pointer + count), for the get(bid, span) overload below
+template<typename T>
+class span {
+public:
+  span(T* p, size_t n): p_(p), n_(n) {}
+  T*     data() const { return p_; }
+  size_t size() const { return n_; }
+
+private:
+  T*     p_;
+  size_t n_;
+};
+
 // Dense block provider: get(block id, buffer) delivers one row-major block
 // (ccsd_t_all_fused_doubles1.hpp:222 `d_t2.get({p4b - noab, p5b - noab, h7b, h1b}, k_a)`).
 template<typename T>
@@ -66,10 +80,23 @@ public:
     ++num_gets;
     fetch_(bid, buf);
   }
+  // span flavour (used by the adapter test when CCSDT_B200_SPAN_TYPE is defined): the provider writes into foreign memory
+  void get(const IndexVector& bid, span<T> out) const {
+    ++num_gets;
+    if(span_fetch_) span_fetch_(bid, out.data(), out.size());
+    else {
+      std::vector<T> tmp;
+      fetch_(bid, tmp);
+      std::copy(tmp.begin(), tmp.begin() + (std::ptrdiff_t) out.size(), out.data());
+    }
+  }
+  using SpanFetch = std::function<void(const IndexVector&, T*, size_t)>;
+  void set_span_fetch(SpanFetch f) { span_fetch_ = std::move(f); }
   mutable size_t num_gets = 0;
 
 private:
-  Fetch fetch_;
+  Fetch     fetch_;
+  SpanFetch span_fetch_;
 };
 
 // LRU cache keyed by block-id vectors.  Call sites:

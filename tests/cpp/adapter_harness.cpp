@@ -5,9 +5,13 @@
 // Links against exachem_b200/libccsdt_b200.so; nothing here computes.
 #include "tamm/tamm.hpp"
 
+#include <cstring>
 #include <stdexcept>
 
 #define CCSDT_B200_TERMINATE(msg) throw std::runtime_error(msg)
+#ifndef ADAPTER_VECTOR_GET // default: the span flavour of Tensor::get (blocks land in the library's pinned buffer)
+#define CCSDT_B200_SPAN_TYPE tamm::span
+#endif
 #include "ccsd_t_fused_driver_b200.hpp"
 
 namespace {
@@ -35,7 +39,7 @@ Space make_space(int noab, int nvab, const int64_t* k_range, const int32_t* k_sp
 
 // a TAMM-like tensor over a dense row-major spin-orbital array; kinds[d] in {'o','v'}
 Tensor<double> dense_tensor(const Space& s, const double* data, std::string kinds) {
-  return Tensor<double>([&s, data, kinds](const IndexVector& bid, std::vector<double>& buf) {
+  auto copy_block = [&s, data, kinds](const IndexVector& bid, std::vector<double>* vec, double* raw) {
     const int d = (int) kinds.size();
     size_t    ext[4], off[4], stride[4], st = 1, n = 1;
     for(int i = d - 1; i >= 0; i--) {
@@ -47,15 +51,22 @@ Tensor<double> dense_tensor(const Space& s, const double* data, std::string kind
       st *= occ ? s.Ot : s.Vt;
       n *= ext[i];
     }
-    if(buf.size() < n) buf.resize(n);
+    if(vec && vec->size() < n) vec->resize(n);
+    double* buf = vec ? vec->data() : raw;
+    // rows of the last index are contiguous in the dense array: one memcpy per row (a local TAMM block read is a
+    // plain copy too; an element-by-element stand-in would dominate the end-to-end time of the adapter)
+    const size_t        row = ext[d - 1], nrows = n / row;
     std::vector<size_t> idx(d, 0);
-    for(size_t lin = 0; lin < n; lin++) {
-      size_t o = 0;
-      for(int i = 0; i < d; i++) o += (off[i] + idx[i]) * stride[i];
-      buf[lin] = data[o];
-      for(int i = d - 1; i >= 0 && ++idx[i] == ext[i]; i--) idx[i] = 0;
+    for(size_t r = 0; r < nrows; r++) {
+      size_t o = off[d - 1];
+      for(int i = 0; i < d - 1; i++) o += (off[i] + idx[i]) * stride[i];
+      std::memcpy(&buf[r * row], data + o, row * sizeof(double));
+      for(int i = d - 2; i >= 0 && ++idx[i] == ext[i]; i--) idx[i] = 0;
     }
-  });
+  };
+  Tensor<double> t([copy_block](const IndexVector& bid, std::vector<double>& buf) { copy_block(bid, &buf, nullptr); });
+  t.set_span_fetch([copy_block](const IndexVector& bid, double* out, size_t) { copy_block(bid, nullptr, out); });
+  return t;
 }
 
 std::string g_error;

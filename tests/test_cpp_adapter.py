@@ -18,11 +18,13 @@ GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_small.json")))
 _dp, _i64p, _i32p = _lib._dp, _lib._i64p, _lib._i32p
 
 
-def harness():
-    if not os.path.exists(SO):   # on the GPU box the prebuilt file travels with the snapshot
+def harness(vector_get=False):
+    """vector_get: the harness built with the std::vector flavour of Tensor::get instead of the span flavour"""
+    so = SO.replace("libadapter_test.so", "libadapter_test_vec.so") if vector_get else SO
+    if not os.path.exists(so):   # on the GPU box the prebuilt file travels with the snapshot
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp")], stdout=subprocess.DEVNULL)
     _lib.load()
-    L = C.CDLL(SO)
+    L = C.CDLL(so)
     L.adapter_last_error.restype = C.c_char_p
     L.adapter_ccsdt_execute.restype = C.c_int
     L.adapter_ccsdt_execute.argtypes = [C.c_int] * 4 + [_i64p, _i32p] + [_dp] * 6 + [C.c_int, C.c_int, _dp, _i64p,
@@ -71,10 +73,12 @@ def test_adapter_fails_loudly_without_gpu():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("vector_get", [False, True])
 @pytest.mark.parametrize("name", sorted(GOLD))
-def test_adapter_execute_matches_reference_fixture(name):
-    """same call as ccsd_t.cpp:253-256 on the tensors the committed reference fixture was made from"""
-    L = harness()
+def test_adapter_execute_matches_reference_fixture(name, vector_get):
+    """same call as ccsd_t.cpp:253-256 on the tensors the committed reference fixture was made from; both flavours of
+    Tensor::get (span: blocks land in the library's pinned buffer; std::vector: one extra host copy)"""
+    L = harness(vector_get)
     g = GOLD[name]
     sp = drv.setup_mo_space(g["noa"], g["nob"], g["nva"], g["nvb"], g["tilesize"])
     T = syn.dense_all(syn.Orbitals(g["noa"], g["nob"], g["nva"], g["nvb"]), g["seed"])
