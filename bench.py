@@ -351,7 +351,10 @@ def main():
                                                                    (", static LPT split" if args.static else ", shared-counter dynamic hand-out")),
                        "l2_policy": "inputs larger than L2: the operand panels of one task (0.4-2.7 GB) exceed the 126 MB L2 "
                                     "and are rebuilt per task",
-                       "cta_box": args.sub or "default (2,2,2,8,8,8), 3 CTAs/SM"},
+                       "cta_box": args.sub or "default (2,2,2,8,8,8), 3 CTAs/SM",
+                       "series_note": "by the bench contract the N=1 line is BASELINE configs[1] (benzene shape) and the N>1 lines are "
+                                      "configs[4] ((60,500), the north_star target): different workloads; the single-GPU point of the "
+                                      "N>1 workload is `bench.py --workload synth` (profiles/bench_r01_n1_synth60x500.json, 56.7 TFLOP/s)"},
             "t_wall_s_per_step": dt / args.steps,
             "fraction_of_fp64_peak": value / (world * peak),
             "symmetry": {
