@@ -3,6 +3,10 @@
   * oracle/_build/libccsdt_oracle.so  -- the C restatement (oracle/ccsdt_oracle.c), class `Oracle`
   * oracle/_ref/libccsdt_ref.so       -- the reference's own (T) path compiled unmodified against the
                                          TAMM shim (oracle/ref_driver.cpp), class `Reference`
+  * oracle/_ref/libccsdt_refgpu_{tc,fma}.so -- the reference's own GPU task function and kernels (K1 DMMA, K2 FMA),
+                                         unmodified, sm_100a, class `ReferenceGPU`: second checker on the GPU box and
+                                         the GPU-side comparator (tests/test_gpu_comparator.py, tools/gpu_comparator.py,
+                                         tools/benzene_real.py)
 and an independent closed-form numpy statement of the 27 equations (`closed_form_energy`,
 SURVEY.md §8 a9/a10) used to cross-check both.
 """
