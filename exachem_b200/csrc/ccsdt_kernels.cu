@@ -22,10 +22,9 @@ namespace ccsdt {
 // =================================================================================================
 // panel build
 // =================================================================================================
-// Small blocks (128 threads x 32 registers) for the staging kernels: they slot into whatever an SM has free
-// while the fused kernel of the previous task drains (they cannot join an SM that holds three fused CTAs,
-// tools/probes/coresidency.cu).
-__global__ void __launch_bounds__(128, 16) gather_panels_kernel(const GatherDesc* __restrict__ descs,
+// (The staging kernels cannot join an SM that holds three fused CTAs -- tools/probes/coresidency.cu -- so the panel
+// build runs in the gap between two fused kernels and is sized for speed, not for co-residency.)
+__global__ void __launch_bounds__(256) gather_panels_kernel(const GatherDesc* __restrict__ descs,
                                                                 SynthInfo si) {
   const GatherDesc& d  = descs[blockIdx.y];
   const int64_t     n3 = d.n[3], n2 = d.n[2], n1 = d.n[1];
@@ -55,12 +54,12 @@ __global__ void __launch_bounds__(128, 16) gather_panels_kernel(const GatherDesc
 cudaError_t launch_gather(const GatherDesc* dev_descs, int ndesc, int64_t max_elems, SynthInfo si,
                           cudaStream_t st) {
   if(ndesc <= 0) return cudaSuccess;
-  int64_t bx = (max_elems + 128 * 8 - 1) / (128 * 8);
+  int64_t bx = (max_elems + 256 * 8 - 1) / (256 * 8);
   if(bx < 1) bx = 1;
-  if(bx > 2048) bx = 2048;
+  if(bx > 1024) bx = 1024;
   for(int off = 0; off < ndesc; off += 65535) {
     const int n = ndesc - off < 65535 ? ndesc - off : 65535;
-    gather_panels_kernel<<<dim3((unsigned) bx, (unsigned) n), 128, 0, st>>>(dev_descs + off, si);
+    gather_panels_kernel<<<dim3((unsigned) bx, (unsigned) n), 256, 0, st>>>(dev_descs + off, si);
   }
   return cudaGetLastError();
 }
