@@ -609,12 +609,9 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
 
 cudaError_t fused_dmma_configure(size_t smem_bytes) {
   cudaError_t e;
-  // Every kernel of a run asks for the same L1/shared-memory split (all shared): CTAs of kernels that prefer
-  // different carve-outs cannot share an SM, and the staging kernels are meant to run next to the fused CTAs.
+  // the fused kernel wants all of the L1/shared-memory array as shared memory (the staging kernels keep the default
+  // split: they run between fused kernels, never next to them, and their strided reads like the larger L1)
   const int carve = (int) cudaSharedmemCarveoutMaxShared;
-  if((e = cudaFuncSetAttribute(gather_panels_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
-  if((e = cudaFuncSetAttribute(zero_words_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
-  if((e = cudaFuncSetAttribute(reduce_partials_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
   if((e = cudaFuncSetAttribute(fused_t_dmma_kernel<160, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
   if((e = cudaFuncSetAttribute(fused_t_dmma_kernel<288, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
   if((e = cudaFuncSetAttribute(fused_t_dmma_kernel<416, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve)) != cudaSuccess) return e;
