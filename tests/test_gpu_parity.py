@@ -413,3 +413,24 @@ def test_v2_tensors_from_cholesky_vectors_on_the_device(orc, cfg):
     assert _close(e1, ref[0]) and _close(e2, ref[1])
     assert np.allclose(pt, ref[2], rtol=1e-11, atol=ATOL)
     assert np.allclose(pt, dense[3], rtol=1e-12, atol=1e-12)
+
+
+def test_random_shapes_symmetric_dmma_kernel_equals_elementwise_kernel():
+    """30 seeded random problems (odd and tiny tiles, one-orbital tiles, unequal alpha/beta, restricted and not): the
+    product kernel with the symmetry reduction against the diagnostic one-thread-per-element kernel, task by task"""
+    rng = np.random.default_rng(20261017)
+    for trial in range(30):
+        restricted = bool(rng.integers(0, 2))
+        oa = int(rng.integers(1, 8))
+        ob = oa if restricted else int(rng.integers(1, 8))
+        va = int(rng.integers(2, 20))
+        vb = va if restricted else int(rng.integers(2, 20))
+        ts = int(rng.integers(1, 12))
+        sp = drv.setup_mo_space(oa, ob, va, vb, ts)
+        if len(drv.enumerate_tasks(sp, restricted)[0]) == 0:
+            continue
+        T = syn.dense_all(syn.Orbitals(oa, ob, va, vb), 1000 + trial)
+        a = run_gpu(sp, T, restricted, symmetry=1)
+        b = run_gpu(sp, T, restricted, kernel=drv.KERNEL_SIMPLE)
+        assert np.allclose(a[3], b[3], rtol=1e-11, atol=1e-13), (trial, oa, ob, va, vb, ts, restricted)
+        assert a[2]["counted_flops"] == b[2]["counted_flops"]
