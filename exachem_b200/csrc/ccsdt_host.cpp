@@ -96,11 +96,12 @@ int make_tiles(int64_t n_occ_alpha, int64_t n_occ_beta, int64_t n_vir_alpha, int
     for(int64_t left = n[g]; left > 0; left -= tilesize, c++) k_range.push_back(std::min(left, tilesize));
     counts[g] = c;
   }
-  // spins: first half of the occupied (virtual) tiles alpha, second half beta -- the reference does
-  // not look at the actual alpha/beta tile counts here
-  const int noab = counts[0] + counts[1], nvab = counts[2] + counts[3];
-  for(int x = 0; x < noab; x++) k_spin.push_back(x < noab / 2 ? 1 : 2);
-  for(int x = 0; x < nvab; x++) k_spin.push_back(x < nvab / 2 ? 1 : 2);
+  // spins by tile count.  The reference labels the first noab/2 (nvab/2) tiles alpha and the rest beta
+  // (ccsd_t.cpp:245-249), which is the actual layout only when both spins have the same number of tiles (or beta
+  // one more); the labels here agree with it in those cases and stay correct for open-shell spaces with
+  // different alpha / beta tile counts (row f5 of SURVEY.md 8f).
+  for(int g = 0; g < 4; g++)
+    for(int x = 0; x < counts[g]; x++) k_spin.push_back(g % 2 ? 2 : 1);
   return (int) k_range.size();
 }
 

@@ -50,10 +50,13 @@ ORC_API int orc_tiles(int64_t n_occ_alpha, int64_t n_occ_beta, int64_t n_vir_alp
   n += counts[3];
   int noab = counts[0] + counts[1], nvab = counts[2] + counts[3];
   int k    = 0;
-  for(int x = 0; x < noab / 2; x++) k_spin[k++] = 1;
-  for(int x = noab / 2; x < noab; x++) k_spin[k++] = 2;
-  for(int x = 0; x < nvab / 2; x++) k_spin[k++] = 1;
-  for(int x = nvab / 2; x < nvab; x++) k_spin[k++] = 2;
+  /* The reference labels the first noab/2 (nvab/2) tiles alpha and the rest beta (ccsd_t.cpp:245-249), which is the
+   * actual tile layout only when both spins have the same number of tiles (or beta has one more).  Here the labels
+   * follow the tile counts, so open-shell spaces with different numbers of alpha and beta tiles are labelled
+   * correctly (row f5 of SURVEY.md 8f); whenever the reference's split is valid the two agree. */
+  (void) noab; (void) nvab;
+  for(int g = 0; g < 4; g++)
+    for(int x = 0; x < counts[g]; x++) k_spin[k++] = (g % 2) ? 2 : 1;
   return n;
 }
 

@@ -173,3 +173,71 @@ def test_gpu_benzene_real_amplitudes_match_the_reference_cpu_energy():
     if "benzene_ccpvdz" in REFE:
         r = REFE["benzene_ccpvdz"]
         assert abs(e1 - r["E[T]"]) <= ATOL and abs(e2 - r["E(T)"]) <= ATOL, (e1, e2, r)
+
+
+def test_unrestricted_task_list_gives_the_restricted_energy_on_h2o():
+    """closed-shell data through the open-shell code path: is_restricted=false enumerates all four spin cases without the
+    factor 2 (ccsd_t_fused_driver.hpp:383-395) and must reproduce the restricted energies"""
+    from oracle.oracle import Oracle
+    fx, _ = fixture("h2o_ccpvdz")
+    T = pv.spin_orbital_tensors(fx)
+    orc = Oracle()
+    sp = orc.tiles(5, 5, 19, 19, 7)
+    r = orc.run(sp, T, True)
+    u = orc.run(sp, T, False)
+    assert abs(r[0] - u[0]) < 1e-13 and abs(r[1] - u[1]) < 1e-13
+    assert abs(r[1] - REFE["h2o_ccpvdz"]["E(T)"]) < 1e-13
+
+
+@pytest.mark.gpu
+def test_gpu_unrestricted_task_list_gives_the_restricted_energy_on_h2o():
+    from exachem_b200 import driver as drv
+    fx, _ = fixture("h2o_ccpvdz")
+    T = pv.spin_orbital_tensors(fx)
+    sp = drv.setup_mo_space(5, 5, 19, 19, 7)
+    d = drv.CCSD_T_Fused_Driver(device=0)
+    e1, e2, _, _ = d.execute(None, None, sp.k_spin, sp, T["t1"], T["t2"], {k: T[k] for k in ("v2ijab", "v2ijka", "v2iabc")},
+                             T["evl"], 0.0, False)
+    r = REFE["h2o_ccpvdz"]
+    assert abs(e1 - r["E[T]"]) <= ATOL and abs(e2 - r["E(T)"]) <= ATOL
+
+
+def _ch2():
+    fx = np.load(os.path.join(HERE, "golden", "ch2_triplet_321g.npz"))
+    T = {k: fx[k] for k in ("evl", "t1", "t2", "v2ijab", "v2ijka", "v2iabc")}
+    return T, json.loads(str(fx["summary"]))
+
+
+def test_open_shell_ch2_triplet_oracle_reference_and_unequal_tile_counts():
+    """row f5: triplet CH2 (UHF, 5 alpha / 3 beta occupied) -- one tile per spin block reproduces the reference CPU path;
+    tilings with DIFFERENT numbers of alpha and beta tiles (which the reference's half/half k_spin rule, ccsd_t.cpp:245-249,
+    mislabels) give the same energy and the closed form of the 27 equations"""
+    from oracle.oracle import Oracle, closed_form_energy
+    T, info = _ch2()
+    na, nb, n = info["n_occ_alpha"], info["n_occ_beta"], info["nbf"]
+    assert abs(info["s_squared"] - 2.0) < 0.05                       # a triplet
+    orc = Oracle()
+    r = REFE["ch2_triplet_321g"]
+    e40 = orc.run(orc.tiles(na, nb, n - na, n - nb, 40), T, False)
+    assert abs(e40[0] - r["E[T]"]) < 1e-14 and abs(e40[1] - r["E(T)"]) < 1e-14
+    c = closed_form_energy(na, nb, n - na, n - nb, T, False)
+    for ts in (4, 3, 2):                                             # occ alpha/beta tiles 2/1, 2/1, 3/2
+        sp = orc.tiles(na, nb, n - na, n - nb, ts)
+        assert sp.noa != sp.nob
+        assert list(sp.k_spin[:sp.noab]) == [1] * sp.noa + [2] * sp.nob
+        e = orc.run(sp, T, False)
+        assert abs(e[0] - c[0]) < 1e-14 and abs(e[1] - c[1]) < 1e-14 and abs(e[1] - r["E(T)"]) < 1e-14
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ts", [40, 4, 3, 2])
+def test_gpu_open_shell_ch2_triplet(ts):
+    from exachem_b200 import driver as drv
+    T, info = _ch2()
+    na, nb, n = info["n_occ_alpha"], info["n_occ_beta"], info["nbf"]
+    sp = drv.setup_mo_space(na, nb, n - na, n - nb, ts)
+    d = drv.CCSD_T_Fused_Driver(device=0)
+    e1, e2, _, _ = d.execute(None, None, sp.k_spin, sp, T["t1"], T["t2"], {k: T[k] for k in ("v2ijab", "v2ijka", "v2iabc")},
+                             T["evl"], 0.0, False)
+    r = REFE["ch2_triplet_321g"]
+    assert abs(e1 - r["E[T]"]) <= ATOL and abs(e2 - r["E(T)"]) <= ATOL, (ts, e1, e2, r)

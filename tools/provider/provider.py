@@ -99,9 +99,9 @@ def _sph_from_cart(l):
 
 
 class Molecule:
-    def __init__(self, input_json, basis_dir):
+    def __init__(self, input_json, basis_dir, basisset=None):
         self.atoms, self.input = read_geometry(input_json)
-        name = self.input["basis"]["basisset"].lower()
+        name = (basisset or self.input["basis"]["basisset"]).lower()
         bas = read_g94(os.path.join(basis_dir, name + ".g94"), {a for a, _ in self.atoms})
         centre, l, nprim, poff, coff, exps, coefs, blocks = [], [], [], [], [], [], [], []
         nc = 0
@@ -189,6 +189,76 @@ def rhf(S, H, eri, nocc, enuc, conv=1e-12, maxiter=200):
             break
         Eold = E
     return E, e, Cm, it + 1
+
+
+def uhf(S, H, eri, na, nb, enuc, conv=1e-12, maxiter=300):
+    """unrestricted Hartree-Fock with DIIS; returns E, (eps_a, eps_b), (C_a, C_b), iterations"""
+    s, Us = np.linalg.eigh(S)
+    X = Us @ np.diag(s ** -0.5) @ Us.T
+    def diag(F):
+        e, Cp = np.linalg.eigh(X.T @ F @ X)
+        return e, X @ Cp
+    ea, Ca = diag(H)
+    eb, Cb = ea.copy(), Ca.copy()
+    if na != nb:   # break the alpha/beta symmetry of the core guess a little
+        Cb = Cb.copy(); Cb[:, [nb - 1, nb]] = Cb[:, [nb, nb - 1]]
+    hist_f, hist_e, Eold = [], [], 0.0
+    for it in range(maxiter):
+        Da, Db = Ca[:, :na] @ Ca[:, :na].T, Cb[:, :nb] @ Cb[:, :nb].T
+        J = np.einsum("pqrs,rs->pq", eri, Da + Db)
+        Fa = H + J - np.einsum("prqs,rs->pq", eri, Da)
+        Fb = H + J - np.einsum("prqs,rs->pq", eri, Db)
+        E = 0.5 * (np.sum((Da + Db) * H) + np.sum(Da * Fa) + np.sum(Db * Fb)) + enuc
+        err = np.concatenate([(X.T @ (Fa @ Da @ S - S @ Da @ Fa) @ X).ravel(), (X.T @ (Fb @ Db @ S - S @ Db @ Fb) @ X).ravel()])
+        hist_f.append((Fa, Fb)); hist_e.append(err)
+        hist_f, hist_e = hist_f[-10:], hist_e[-10:]
+        if len(hist_f) > 1:
+            m = len(hist_f)
+            B = -np.ones((m + 1, m + 1)); B[m, m] = 0
+            for i in range(m):
+                for j in range(m):
+                    B[i, j] = hist_e[i] @ hist_e[j]
+            rhs = np.zeros(m + 1); rhs[m] = -1
+            c = np.linalg.solve(B, rhs)[:m]
+            Fa = sum(ci * f[0] for ci, f in zip(c, hist_f))
+            Fb = sum(ci * f[1] for ci, f in zip(c, hist_f))
+        ea, Ca = diag(Fa)
+        eb, Cb = diag(Fb)
+        if abs(E - Eold) < conv and np.abs(err).max() < 1e-9:
+            break
+        Eold = E
+    return E, (ea, eb), (Ca, Cb), it + 1
+
+
+def solve_uhf(input_json, basis_dir, multiplicity, basisset=None, verbose=True):
+    """open-shell route: integrals -> UHF -> spin-orbital CCSD.  Returns the dense spin-orbital tensors in the reference's
+    layout (| occ a | occ b | virt a | virt b |) and a summary; [T]/(T) need is_restricted = false."""
+    mol = Molecule(input_json, basis_dir, basisset)
+    S, T, V, eri = mol.integrals()
+    nb = (mol.nelec - (multiplicity - 1)) // 2
+    na = mol.nelec - nb
+    escf, (ea, eb), (Ca, Cb), it_scf = uhf(S, T + V, eri, na, nb, mol.nuclear_repulsion())
+    n = len(ea)
+    Cso = np.concatenate([Ca[:, :na], Cb[:, :nb], Ca[:, na:], Cb[:, nb:]], axis=1)       # spatial parts, tile order
+    spin = np.array([0] * na + [1] * nb + [0] * (n - na) + [1] * (n - nb))
+    eso = np.concatenate([ea[:na], eb[:nb], ea[na:], eb[nb:]])
+    g = np.einsum("pqrs,pi,qj,rk,sl->ijkl", eri, Cso, Cso, Cso, Cso, optimize=True)       # (ij|kl) over spin orbitals
+    same = (spin[:, None] == spin[None, :]).astype(float)
+    g = g * same[:, :, None, None] * same[None, None, :, :]
+    phys = g.transpose(0, 2, 1, 3)
+    anti = phys - phys.transpose(0, 1, 3, 2)
+    no = na + nb
+    ecc, t1, t2, it_cc = ccsd(anti, eso, no, verbose=False)
+    o, v = slice(0, no), slice(no, None)
+    c = np.ascontiguousarray
+    tensors = dict(evl=eso, t1=c(t1.T), t2=c(t2.transpose(2, 3, 0, 1)), v2ijab=c(anti[o, o, v, v]),
+                   v2ijka=c(anti[o, o, o, v]), v2iabc=c(anti[o, v, v, v]))
+    s2 = 0.25 * (na - nb) * (na - nb + 2) + nb - np.sum((Ca[:, :na].T @ S @ Cb[:, :nb]) ** 2)
+    info = dict(nbf=int(n), n_occ_alpha=int(na), n_occ_beta=int(nb), e_nuc=float(mol.nuclear_repulsion()), e_scf=float(escf),
+                e_ccsd_corr=float(ecc), s_squared=float(s2), scf_iterations=int(it_scf), ccsd_iterations=int(it_cc))
+    if verbose:
+        print(info)
+    return tensors, info
 
 
 # ------------------------------------------------------------------------------------------------ CD
