@@ -105,6 +105,7 @@ struct ccsdt_ctx {
   void*        encode_fn = nullptr;
   int64_t*     task_counter = nullptr; // process-shared dynamic task counter (NULL = static split)
   ccsdt_stats  stats{};
+  int64_t      pending_h2d = 0; // bytes uploaded by ccsdt_put_* since the last run
   // symmetry-reduced box lists (device), keyed by (nbox, brick, nbrick, sym): a handful per job
   struct BoxList {
     int32_t* dev = nullptr;
@@ -804,6 +805,8 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
   cudaSetDevice(ctx->device);
   const auto t0 = std::chrono::high_resolution_clock::now();
   ctx->stats    = ccsdt_stats{};
+  ctx->stats.h2d_bytes = ctx->pending_h2d; // uploads (ccsdt_put_*) since the previous run belong to this one
+  ctx->pending_h2d     = 0;
   energies[0] = energies[1] = 0.0;
   const int64_t nids = (int64_t) ids.size();
 
@@ -1250,7 +1253,7 @@ int ccsdt_put_cholesky(ccsdt_ctx* ctx, const double* host_chol, int64_t ncv) {
   const size_t nchol = (size_t) N * N * ncv;
   CK(cudaMalloc(&d_chol, nchol * 8));
   CK(cudaMemcpyAsync(d_chol, host_chol, nchol * 8, cudaMemcpyHostToDevice, st));
-  ctx->stats.h2d_bytes += (int64_t) nchol * 8;
+  ctx->pending_h2d += (int64_t) nchol * 8;
   CK(cudaMalloc(&Loo, (size_t) O * O * ncv * 8));
   CK(cudaMalloc(&Lov, (size_t) O * V * ncv * 8));
   CK(cudaMalloc(&Lvv, (size_t) V * V * ncv * 8));
@@ -1294,14 +1297,61 @@ int ccsdt_put_dense(ccsdt_ctx* ctx, int tensor, const double* host) {
     CK(cudaFree(ctx->dense[tensor]));
     ctx->dense[tensor] = nullptr;
   }
+  CK(cudaStreamSynchronize(ctx->s_compute)); // a running task may still read the old contents
+  CK(cudaStreamSynchronize(ctx->s_compute2));
   if(!ctx->dense[tensor]) {
     CK(cudaMalloc(&ctx->dense[tensor], n * 8));
     ctx->dense_elems[tensor] = n;
+    CK(cudaMemsetAsync(ctx->dense[tensor], 0, n * 8, ctx->s_stage)); // spin-forbidden blocks stay zero for good
   }
-  CK(cudaStreamSynchronize(ctx->s_compute)); // a running task may still read the old contents
-  CK(cudaMemcpyAsync(ctx->dense[tensor], host, n * 8, cudaMemcpyHostToDevice, ctx->s_stage));
+  // Only the spin-conserving blocks cross the bus: T1[a,i] with s_a = s_i, four-index tensors with
+  // s_0 + s_1 = s_2 + s_3 (6 of the 16 spin patterns).  These are the only blocks any enabled term of any task
+  // reads -- and the only ones the reference ever requests through Tensor::get -- so the rest of the dense host
+  // array is never looked at.  One strided 3-d copy per (leading index, spin pattern).
+  const char*  kinds = kKinds[tensor];
+  const int    nd    = (int) strlen(kinds);
+  int64_t      full[4] = {1, 1, 1, 1}, lo[4][2], len[4][2];
+  for(int d = 0; d < nd; d++) {
+    const bool virt = kinds[d] == 'v';
+    full[d]         = dim_full(ctx->sp, kinds[d]);
+    int     tb, te;
+    int64_t na = 0, nbeta = 0;
+    ctx->sp.spin_range(virt, 1, tb, te, na);
+    ctx->sp.spin_range(virt, 2, tb, te, nbeta);
+    lo[d][0] = 0, len[d][0] = na, lo[d][1] = na, len[d][1] = nbeta;
+  }
+  int64_t sent = 0;
+  if(nd == 2) {
+    for(int s0 = 0; s0 < 2; s0++) {
+      if(len[0][s0] <= 0 || len[1][s0] <= 0) continue;
+      const int64_t off = lo[0][s0] * full[1] + lo[1][s0];
+      CK(cudaMemcpy2DAsync(ctx->dense[tensor] + off, (size_t) full[1] * 8, host + off, (size_t) full[1] * 8,
+                           (size_t) len[1][s0] * 8, (size_t) len[0][s0], cudaMemcpyHostToDevice, ctx->s_stage));
+      sent += len[0][s0] * len[1][s0] * 8;
+    }
+  }
+  else {
+    for(int pat = 0; pat < 16; pat++) {
+      const int sp_[4] = {(pat >> 3) & 1, (pat >> 2) & 1, (pat >> 1) & 1, pat & 1};
+      if(sp_[0] + sp_[1] != sp_[2] + sp_[3]) continue;
+      bool empty = false;
+      for(int d = 0; d < 4; d++) empty |= len[d][sp_[d]] <= 0;
+      if(empty) continue;
+      for(int64_t i0 = lo[0][sp_[0]]; i0 < lo[0][sp_[0]] + len[0][sp_[0]]; i0++) {
+        const int64_t    off = ((i0 * full[1] + lo[1][sp_[1]]) * full[2] + lo[2][sp_[2]]) * full[3] + lo[3][sp_[3]];
+        cudaMemcpy3DParms cp{};
+        cp.srcPtr = make_cudaPitchedPtr((void*) (host + off), (size_t) full[3] * 8, (size_t) full[3] * 8, (size_t) full[2]);
+        cp.dstPtr = make_cudaPitchedPtr((void*) (ctx->dense[tensor] + off), (size_t) full[3] * 8, (size_t) full[3] * 8,
+                                        (size_t) full[2]);
+        cp.extent = make_cudaExtent((size_t) len[3][sp_[3]] * 8, (size_t) len[2][sp_[2]], (size_t) len[1][sp_[1]]);
+        cp.kind   = cudaMemcpyHostToDevice;
+        CK(cudaMemcpy3DAsync(&cp, ctx->s_stage));
+        sent += len[1][sp_[1]] * len[2][sp_[2]] * len[3][sp_[3]] * 8;
+      }
+    }
+  }
   CK(cudaStreamSynchronize(ctx->s_stage));   // the caller may reuse `host` on return
-  ctx->stats.h2d_bytes += (int64_t) n * 8;
+  ctx->pending_h2d += sent;                  // reported by the next run's stats
   ctx->synthetic = false;
   return 0;
 }
@@ -1326,7 +1376,7 @@ int ccsdt_put_block(ccsdt_ctx* ctx, int tensor, const uint32_t bid[4], const dou
   }
   else dev = it->second.dev;
   CK(cudaMemcpy(dev, host, n * 8, cudaMemcpyHostToDevice));
-  ctx->stats.h2d_bytes += (int64_t) n * 8;
+  ctx->pending_h2d += (int64_t) n * 8;
   ctx->synthetic = false;
   return 0;
 }

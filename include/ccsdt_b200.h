@@ -93,7 +93,7 @@ typedef struct ccsdt_stats {
   double  seconds_total;      /* wall time of ccsdt_run */
   double  seconds_kernel;     /* CUDA-event time of the fused kernel launches (sum) */
   double  seconds_staging;    /* CUDA-event time of the panel-build launches (sum) */
-  int64_t h2d_bytes, d2h_bytes;
+  int64_t h2d_bytes, d2h_bytes; /* h2d includes the uploads (ccsdt_put_*) made since the previous run */
   int64_t blocks_fetched;     /* fetch-callback invocations */
   double  evaluated_flops;    /* counted_flops x (CTA boxes evaluated / CTA boxes of the tile): what the fused kernel
                                  had to execute after the symmetry reduction (== counted_flops with symmetry = 0) */
@@ -133,7 +133,9 @@ CCSDT_API int     ccsdt_box_weight(int sym, const int32_t box[6]);
 CCSDT_API int ccsdt_set_space(ccsdt_ctx* ctx, int noa, int nob, int nva, int nvb, const int64_t* k_range,
                     const int32_t* k_spin, const double* evl, int is_restricted);
 
-/* operand supply (choose one per tensor) */
+/* operand supply (choose one per tensor).  ccsdt_put_dense copies only the spin-conserving blocks of the dense host array
+ * (T1: s_a = s_i; four-index tensors: s_0 + s_1 = s_2 + s_3 -- the only blocks any task reads and the only ones the
+ * reference requests through Tensor::get); the other blocks of the device copy are zero. */
 CCSDT_API int ccsdt_put_dense(ccsdt_ctx* ctx, int tensor, const double* host_dense);
 CCSDT_API int ccsdt_put_block(ccsdt_ctx* ctx, int tensor, const uint32_t bid[4], const double* host_block);
 CCSDT_API int ccsdt_set_fetch(ccsdt_ctx* ctx, ccsdt_fetch_fn fn, void* user);
