@@ -45,6 +45,7 @@ SIGNATURES = {
     "ccsdt_box_weight": (C.c_int, [C.c_int, _i32p]),
     "ccsdt_set_space": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [_i64p, _i32p, _dp, C.c_int]),
     "ccsdt_put_dense": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "ccsdt_put_dense_async": (C.c_int, [C.c_void_p, C.c_int, _dp]),
     "ccsdt_put_block": (C.c_int, [C.c_void_p, C.c_int, _u32p, _dp]),
     "ccsdt_set_fetch": (C.c_int, [C.c_void_p, FETCH_FN, C.c_void_p]),
     "ccsdt_set_synthetic": (C.c_int, [C.c_void_p, C.c_uint64]),

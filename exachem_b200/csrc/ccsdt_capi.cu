@@ -83,6 +83,7 @@ struct ccsdt_ctx {
 
   double*                        dense[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t                         dense_elems[5] = {0, 0, 0, 0, 0};
+  bool                           dense_sparse_ok[5] = {false, false, false, false, false}; // spin-forbidden blocks are zero
   std::map<BlockKey, BlockEntry> blocks;
   size_t                         block_bytes = 0, block_budget = 0;
   int64_t                        use_clock = 0;
@@ -106,6 +107,11 @@ struct ccsdt_ctx {
   int64_t*     task_counter = nullptr; // process-shared dynamic task counter (NULL = static split)
   ccsdt_stats  stats{};
   int64_t      pending_h2d = 0; // bytes uploaded by ccsdt_put_* since the last run
+  // asynchronous dense uploads (ccsdt_put_dense_async): the all-alpha blocks of every tensor travel on s_copy_a,
+  // the other spin patterns on s_copy_b; tasks whose six tiles are all alpha only wait for the first
+  cudaStream_t s_copy_a = nullptr, s_copy_b = nullptr;
+  cudaEvent_t  ev_alpha[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, ev_full[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool         upload_pending[5] = {false, false, false, false, false};
   // symmetry-reduced box lists (device), keyed by (nbox, brick, nbrick, sym): a handful per job
   struct BoxList {
     int32_t* dev = nullptr;
@@ -744,6 +750,16 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
     sp.spin_range(true, 1, tb, te, n);  si.nva = (int) n;
     sp.spin_range(true, 2, tb, te, n);  si.nvb = (int) n;
   }
+  // asynchronous dense uploads still in flight: an all-alpha task only needs the all-alpha blocks
+  {
+    bool all_alpha = true;
+    for(int i = 0; i < 6; i++) all_alpha &= sp.k_spin[t.t[i]] == 1;
+    for(int tn = 0; tn < 5; tn++)
+      if(ctx->upload_pending[tn]) {
+        CK(cudaStreamWaitEvent(ctx->s_stage, ctx->ev_alpha[tn], 0));
+        if(!all_alpha) CK(cudaStreamWaitEvent(ctx->s_stage, ctx->ev_full[tn], 0));
+      }
+  }
   // the buffer's partials and box-scheduler words are zeroed here, on the staging stream, long before the launch
   // (ids of the padded brick grid that are not boxes are never written: their partials stay zero)
   CK(launch_zero(b.d_partial, 2 * b.nparts, b.d_counter, COUNTER_WORDS, ctx->s_stage));
@@ -835,6 +851,18 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
     for(int64_t k = 0; k < nids; k++)
       if(own[k] == ctx->opt.rank) order.push_back(ids[k]);
   }
+  {
+    // uploads in flight: the tasks that only need the all-alpha blocks (the first to arrive) go first; per-task energies
+    // are summed in canonical order whatever the execution order
+    bool pending = false;
+    for(int tn = 0; tn < 5; tn++) pending |= ctx->upload_pending[tn];
+    if(pending && !ctx->task_counter)
+      std::stable_partition(order.begin(), order.end(), [&](int64_t id) {
+        bool a = true;
+        for(int i = 0; i < 6; i++) a &= ctx->sp.k_spin[ctx->tasks[id].t[i]] == 1;
+        return a;
+      });
+  }
   int64_t cursor = 0;
   auto    next_task = [&]() -> int64_t {
     const int64_t k = ctx->task_counter ? __atomic_fetch_add(ctx->task_counter, (int64_t) 1, __ATOMIC_RELAXED) : cursor++;
@@ -883,6 +911,9 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
                        " (a pipeline timeout traps instead of hanging)", 9);
     }
     CK(cudaStreamSynchronize(ctx->s_stage));
+    CK(cudaStreamSynchronize(ctx->s_copy_a));
+    CK(cudaStreamSynchronize(ctx->s_copy_b));
+    for(int tn = 0; tn < 5; tn++) ctx->upload_pending[tn] = false;
     uint32_t flag = 0;
     CK(cudaMemcpy(&flag, ctx->d_error, 4, cudaMemcpyDeviceToHost));
     if(flag) return ctx->fail("device error flag " + std::to_string(flag), 9);
@@ -972,6 +1003,12 @@ int ccsdt_create(ccsdt_ctx** out, int device) {
   if((e = cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
   if((e = cudaStreamCreateWithFlags(&ctx->s_compute2, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
   if((e = cudaEventCreate(&ctx->ev_base)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  if((e = cudaStreamCreateWithFlags(&ctx->s_copy_a, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  if((e = cudaStreamCreateWithFlags(&ctx->s_copy_b, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  for(int t = 0; t < 5; t++) {
+    if((e = cudaEventCreateWithFlags(&ctx->ev_alpha[t], cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if((e = cudaEventCreateWithFlags(&ctx->ev_full[t], cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  }
   {
     // staging blocks (128 threads x 32 registers) slot in next to the resident fused CTAs; give them priority
     int lo = 0, hi = 0;
@@ -1016,6 +1053,12 @@ int ccsdt_destroy(ccsdt_ctx* ctx) {
   if(ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
   if(ctx->s_compute2) cudaStreamDestroy(ctx->s_compute2);
   if(ctx->ev_base) cudaEventDestroy(ctx->ev_base);
+  if(ctx->s_copy_a) cudaStreamDestroy(ctx->s_copy_a);
+  if(ctx->s_copy_b) cudaStreamDestroy(ctx->s_copy_b);
+  for(int t = 0; t < 5; t++) {
+    if(ctx->ev_alpha[t]) cudaEventDestroy(ctx->ev_alpha[t]);
+    if(ctx->ev_full[t]) cudaEventDestroy(ctx->ev_full[t]);
+  }
   if(ctx->s_stage) cudaStreamDestroy(ctx->s_stage);
   delete ctx;
   return 0;
@@ -1231,6 +1274,7 @@ int dense_alloc(ccsdt_ctx* ctx, int tensor, size_t n) {
     CK(cudaMalloc(&ctx->dense[tensor], n * 8));
     ctx->dense_elems[tensor] = n;
   }
+  ctx->dense_sparse_ok[tensor] = false; // written in full by the caller (ccsdt_put_cholesky)
   return 0;
 }
 
@@ -1285,7 +1329,7 @@ int ccsdt_put_cholesky(ccsdt_ctx* ctx, const double* host_chol, int64_t ncv) {
   return 0;
 }
 
-int ccsdt_put_dense(ccsdt_ctx* ctx, int tensor, const double* host) {
+static int put_dense_impl(ccsdt_ctx* ctx, int tensor, const double* host, bool async) {
   if(!ctx || tensor < 0 || tensor > 4 || !host) return 1;
   if(!ctx->have_space) return ctx->fail("ccsdt_set_space must be called first");
   cudaSetDevice(ctx->device);
@@ -1301,8 +1345,14 @@ int ccsdt_put_dense(ccsdt_ctx* ctx, int tensor, const double* host) {
   CK(cudaStreamSynchronize(ctx->s_compute2));
   if(!ctx->dense[tensor]) {
     CK(cudaMalloc(&ctx->dense[tensor], n * 8));
-    ctx->dense_elems[tensor] = n;
-    CK(cudaMemsetAsync(ctx->dense[tensor], 0, n * 8, ctx->s_stage)); // spin-forbidden blocks stay zero for good
+    ctx->dense_elems[tensor]     = n;
+    ctx->dense_sparse_ok[tensor] = false;
+  }
+  cudaStream_t sa = async ? ctx->s_copy_a : ctx->s_stage, sb = async ? ctx->s_copy_b : ctx->s_stage;
+  if(!ctx->dense_sparse_ok[tensor]) {
+    CK(cudaMemsetAsync(ctx->dense[tensor], 0, n * 8, sa)); // spin-forbidden blocks stay zero for good
+    CK(cudaStreamSynchronize(sa));
+    ctx->dense_sparse_ok[tensor] = true;
   }
   // Only the spin-conserving blocks cross the bus: T1[a,i] with s_a = s_i, four-index tensors with
   // s_0 + s_1 = s_2 + s_3 (6 of the 16 spin patterns).  These are the only blocks any enabled term of any task
@@ -1326,7 +1376,7 @@ int ccsdt_put_dense(ccsdt_ctx* ctx, int tensor, const double* host) {
       if(len[0][s0] <= 0 || len[1][s0] <= 0) continue;
       const int64_t off = lo[0][s0] * full[1] + lo[1][s0];
       CK(cudaMemcpy2DAsync(ctx->dense[tensor] + off, (size_t) full[1] * 8, host + off, (size_t) full[1] * 8,
-                           (size_t) len[1][s0] * 8, (size_t) len[0][s0], cudaMemcpyHostToDevice, ctx->s_stage));
+                           (size_t) len[1][s0] * 8, (size_t) len[0][s0], cudaMemcpyHostToDevice, s0 == 0 ? sa : sb));
       sent += len[0][s0] * len[1][s0] * 8;
     }
   }
@@ -1345,16 +1395,27 @@ int ccsdt_put_dense(ccsdt_ctx* ctx, int tensor, const double* host) {
                                         (size_t) full[2]);
         cp.extent = make_cudaExtent((size_t) len[3][sp_[3]] * 8, (size_t) len[2][sp_[2]], (size_t) len[1][sp_[1]]);
         cp.kind   = cudaMemcpyHostToDevice;
-        CK(cudaMemcpy3DAsync(&cp, ctx->s_stage));
+        CK(cudaMemcpy3DAsync(&cp, pat == 0 ? sa : sb));
         sent += len[1][sp_[1]] * len[2][sp_[2]] * len[3][sp_[3]] * 8;
       }
     }
   }
-  CK(cudaStreamSynchronize(ctx->s_stage));   // the caller may reuse `host` on return
+  if(async) {
+    CK(cudaEventRecord(ctx->ev_alpha[tensor], sa));
+    CK(cudaEventRecord(ctx->ev_full[tensor], sb));
+    ctx->upload_pending[tensor] = true;
+  }
+  else {
+    CK(cudaStreamSynchronize(ctx->s_stage)); // the caller may reuse `host` on return
+    ctx->upload_pending[tensor] = false;
+  }
   ctx->pending_h2d += sent;                  // reported by the next run's stats
   ctx->synthetic = false;
   return 0;
 }
+
+int ccsdt_put_dense(ccsdt_ctx* ctx, int tensor, const double* host) { return put_dense_impl(ctx, tensor, host, false); }
+int ccsdt_put_dense_async(ccsdt_ctx* ctx, int tensor, const double* host) { return put_dense_impl(ctx, tensor, host, true); }
 
 int ccsdt_put_block(ccsdt_ctx* ctx, int tensor, const uint32_t bid[4], const double* host) {
   if(!ctx || tensor < 0 || tensor > 4 || !host || !bid) return 1;

@@ -170,9 +170,15 @@ class Context:
         self._ck(self.L.ccsdt_set_space(self.h, sp.noa, sp.nob, sp.nva, sp.nvb, _p(kr, _lib._i64p),
                                         _p(ks, _lib._i32p), _p(ev, _lib._dp), int(is_restricted)))
 
-    def put_dense(self, tensor: int, arr):
+    def put_dense(self, tensor: int, arr, async_: bool = False):
+        """async_: return without waiting for the copy; `arr` (pinned memory for a truly asynchronous copy) must stay
+        unchanged until the next run returns (a reference is kept here until then)."""
         a = np.ascontiguousarray(arr, np.float64)
-        self._ck(self.L.ccsdt_put_dense(self.h, tensor, _p(a, _lib._dp)))
+        if async_:
+            self._pending_uploads = getattr(self, "_pending_uploads", []) + [a]
+            self._ck(self.L.ccsdt_put_dense_async(self.h, tensor, _p(a, _lib._dp)))
+        else:
+            self._ck(self.L.ccsdt_put_dense(self.h, tensor, _p(a, _lib._dp)))
 
     def put_block(self, tensor: int, bid, arr):
         a = np.ascontiguousarray(arr, np.float64)
@@ -221,6 +227,7 @@ class Context:
         self._ck(self.L.ccsdt_run(self.h, task_begin, task_end, _p(e, _lib._dp),
                                   _p(pt, _lib._dp) if pt is not None else None, C.byref(st)))
         stats = {k: getattr(st, k) for k, _ in Stats._fields_}
+        self._pending_uploads = []
         return float(e[0]), float(e[1]), stats, pt
 
 
@@ -233,6 +240,7 @@ class Context:
         self._ck(self.L.ccsdt_run_tasks(self.h, _p(ids, _lib._i64p), len(ids), _p(e, _lib._dp),
                                         _p(pt, _lib._dp) if pt is not None else None, C.byref(st)))
         stats = {k: getattr(st, k) for k, _ in Stats._fields_}
+        self._pending_uploads = []
         return float(e[0]), float(e[1]), stats, pt
 
 

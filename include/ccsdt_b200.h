@@ -137,6 +137,10 @@ CCSDT_API int ccsdt_set_space(ccsdt_ctx* ctx, int noa, int nob, int nva, int nvb
  * (T1: s_a = s_i; four-index tensors: s_0 + s_1 = s_2 + s_3 -- the only blocks any task reads and the only ones the
  * reference requests through Tensor::get); the other blocks of the device copy are zero. */
 CCSDT_API int ccsdt_put_dense(ccsdt_ctx* ctx, int tensor, const double* host_dense);
+/* Same, without waiting for the copy: host_dense (pinned memory, or the copy is staged) must stay valid and unchanged
+ * until the next ccsdt_run / ccsdt_run_tasks returns.  The all-alpha blocks of every tensor travel first, on their own
+ * stream, and that run starts with the tasks whose six tiles are all alpha while the other spin patterns still arrive. */
+CCSDT_API int ccsdt_put_dense_async(ccsdt_ctx* ctx, int tensor, const double* host_dense);
 CCSDT_API int ccsdt_put_block(ccsdt_ctx* ctx, int tensor, const uint32_t bid[4], const double* host_block);
 CCSDT_API int ccsdt_set_fetch(ccsdt_ctx* ctx, ccsdt_fetch_fn fn, void* user);
 CCSDT_API int ccsdt_set_synthetic(ccsdt_ctx* ctx, uint64_t seed); /* procedural tensors generated on the device */

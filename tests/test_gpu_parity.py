@@ -434,3 +434,25 @@ def test_random_shapes_symmetric_dmma_kernel_equals_elementwise_kernel():
         b = run_gpu(sp, T, restricted, kernel=drv.KERNEL_SIMPLE)
         assert np.allclose(a[3], b[3], rtol=1e-11, atol=1e-13), (trial, oa, ob, va, vb, ts, restricted)
         assert a[2]["counted_flops"] == b[2]["counted_flops"]
+
+
+@pytest.mark.parametrize("cfg", [(6, 6, 17, 17, 5, True), (5, 3, 9, 12, 4, False)])
+def test_asynchronous_dense_upload_gives_identical_energies(cfg):
+    """ccsdt_put_dense_async: copies in flight while the all-alpha tasks already run; same per-task energies as the
+    synchronous upload, bit for bit, and the upload bytes show up in the run's stats"""
+    oa, ob, va, vb, ts, restricted = cfg
+    sp = drv.setup_mo_space(oa, ob, va, vb, ts)
+    T = syn.dense_all(syn.Orbitals(oa, ob, va, vb), 77)
+    sync = run_gpu(sp, T, restricted)
+    n = len(drv.enumerate_tasks(sp, restricted)[0])
+    ctx = drv.Context(0)
+    try:
+        ctx.set_space(sp, T["evl"], restricted)
+        for rep in range(2):          # second pass re-uploads into the same device buffers
+            for tid, k in ((drv.T1, "t1"), (drv.T2, "t2"), (drv.V_IJAB, "v2ijab"), (drv.V_IJKA, "v2ijka"), (drv.V_IABC, "v2iabc")):
+                ctx.put_dense(tid, T[k], async_=True)
+            e1, e2, st, pt = ctx.run(per_task_n=n)
+            assert np.array_equal(pt, sync[3]) and e1 == sync[0] and e2 == sync[1]
+            assert 0 < st["h2d_bytes"] < sum(T[k].nbytes for k in ("t1", "t2", "v2ijab", "v2ijka", "v2iabc"))
+    finally:
+        ctx.close()
