@@ -740,7 +740,8 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
   P.partial = b.d_partial;
 
   // ---- launch the panel build on the staging stream ----
-  CK(cudaMemcpyAsync(b.d_descs, b.h_descs, sizeof(GatherDesc) * nd, cudaMemcpyHostToDevice, ctx->s_stage));
+  static_assert(sizeof(GatherDesc) % 4 == 0, "descriptor copy works in 32-bit words");
+  CK(launch_copy_from_pinned(b.h_descs, b.d_descs, sizeof(GatherDesc) * nd, ctx->s_stage));
   SynthInfo si{ctx->seed, 0, 0, 0, 0};
   {
     int     tb, te;
@@ -767,7 +768,7 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t) {
   CK(launch_gather(b.d_descs, nd, max_elems, si, ctx->s_stage));
   CK(cudaEventRecord(b.g1, ctx->s_stage));
   CK(cudaEventRecord(b.staged, ctx->s_stage));
-  ctx->stats.kernel_launches += 1 + (nd + 65534) / 65535;
+  ctx->stats.kernel_launches += 2 + (nd + 65534) / 65535;
   return 0;
 }
 
@@ -1387,16 +1388,26 @@ static int put_dense_impl(ccsdt_ctx* ctx, int tensor, const double* host, bool a
       bool empty = false;
       for(int d = 0; d < 4; d++) empty |= len[d][sp_[d]] <= 0;
       if(empty) continue;
-      for(int64_t i0 = lo[0][sp_[0]]; i0 < lo[0][sp_[0]] + len[0][sp_[0]]; i0++) {
-        const int64_t    off = ((i0 * full[1] + lo[1][sp_[1]]) * full[2] + lo[2][sp_[2]]) * full[3] + lo[3][sp_[3]];
+      // one 3-d copy per value of the SHORTEST of the three leading indices (fewest calls); rows run along the last
+      // index, the copy's y and z are the two other leading indices A < B with their natural strides
+      const int64_t stride[4] = {full[1] * full[2] * full[3], full[2] * full[3], full[3], 1};
+      int           L = 0;
+      for(int d = 1; d < 3; d++)
+        if(len[d][sp_[d]] < len[L][sp_[L]]) L = d;
+      const int A = L == 0 ? 1 : 0, B = L == 2 ? 1 : 2;
+      int64_t   base = 0;
+      for(int d = 0; d < 4; d++) base += lo[d][sp_[d]] * stride[d];
+      for(int64_t il = 0; il < len[L][sp_[L]]; il++) {
+        const int64_t     off = base + il * stride[L];
         cudaMemcpy3DParms cp{};
-        cp.srcPtr = make_cudaPitchedPtr((void*) (host + off), (size_t) full[3] * 8, (size_t) full[3] * 8, (size_t) full[2]);
-        cp.dstPtr = make_cudaPitchedPtr((void*) (ctx->dense[tensor] + off), (size_t) full[3] * 8, (size_t) full[3] * 8,
-                                        (size_t) full[2]);
-        cp.extent = make_cudaExtent((size_t) len[3][sp_[3]] * 8, (size_t) len[2][sp_[2]], (size_t) len[1][sp_[1]]);
+        cp.srcPtr = make_cudaPitchedPtr((void*) (host + off), (size_t) stride[B] * 8, (size_t) full[3] * 8,
+                                        (size_t) (stride[A] / stride[B]));
+        cp.dstPtr = make_cudaPitchedPtr((void*) (ctx->dense[tensor] + off), (size_t) stride[B] * 8, (size_t) full[3] * 8,
+                                        (size_t) (stride[A] / stride[B]));
+        cp.extent = make_cudaExtent((size_t) len[3][sp_[3]] * 8, (size_t) len[B][sp_[B]], (size_t) len[A][sp_[A]]);
         cp.kind   = cudaMemcpyHostToDevice;
         CK(cudaMemcpy3DAsync(&cp, pat == 0 ? sa : sb));
-        sent += len[1][sp_[1]] * len[2][sp_[2]] * len[3][sp_[3]] * 8;
+        sent += len[A][sp_[A]] * len[B][sp_[B]] * len[3][sp_[3]] * 8;
       }
     }
   }

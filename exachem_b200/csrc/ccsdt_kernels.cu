@@ -14,6 +14,7 @@
 //   probes                 : FP64 DFMA / DMMA peak, DMMA fragment layout, TMA swizzle layout
 #include "ccsdt_kernel_common.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <type_traits>
 
@@ -71,6 +72,22 @@ __global__ void __launch_bounds__(128, 16) zero_words_kernel(double* __restrict_
   const int64_t i0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t) gridDim.x * blockDim.x;
   for(int64_t i = i0; i < na; i += stride) a[i] = 0.0;
   for(int64_t i = i0; i < nb; i += stride) b[i] = 0u;
+}
+
+// copies the gather descriptors of a task from pinned host memory (read through its device alias) to device memory.
+// A cudaMemcpyAsync would queue on the host-to-device copy engine BEHIND any dense upload still in flight
+// (ccsdt_put_dense_async) and hold the first panel build back until the last byte has arrived.
+__global__ void __launch_bounds__(128, 16) copy_words_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t n) {
+  for(int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+cudaError_t launch_copy_from_pinned(const void* pinned_host, void* dev, size_t bytes, cudaStream_t st) {
+  void*       alias = nullptr;
+  cudaError_t e     = cudaHostGetDevicePointer(&alias, const_cast<void*>(pinned_host), 0);
+  if(e != cudaSuccess) return e;
+  const int64_t n = (int64_t) (bytes / 4);
+  copy_words_kernel<<<(unsigned) std::min<int64_t>((n + 127) / 128, 64), 128, 0, st>>>((const uint32_t*) alias, (uint32_t*) dev, n);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_zero(double* a, int64_t na, uint32_t* b, int nb, cudaStream_t st) {
