@@ -1295,6 +1295,13 @@ int ccsdt_put_cholesky(ccsdt_ctx* ctx, const double* host_chol, int64_t ncv) {
   CK(cudaStreamSynchronize(ctx->s_compute2));
   cudaStream_t st = ctx->s_stage;
   double *d_chol = nullptr, *Loo = nullptr, *Lov = nullptr, *Lvv = nullptr, *G = nullptr;
+  struct Scratch { // the temporaries are released on every way out (the CK macro returns on failure)
+    double** p[5];
+    ~Scratch() {
+      for(double** q: p)
+        if(*q) cudaFree(*q);
+    }
+  } scratch{{&d_chol, &Loo, &Lov, &Lvv, &G}};
   const size_t nchol = (size_t) N * N * ncv;
   CK(cudaMalloc(&d_chol, nchol * 8));
   CK(cudaMemcpyAsync(d_chol, host_chol, nchol * 8, cudaMemcpyHostToDevice, st));
@@ -1324,7 +1331,6 @@ int ccsdt_put_cholesky(ccsdt_ctx* ctx, const double* host_chol, int64_t ncv) {
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(st));
   ctx->stats.kernel_launches += 5 + 2 * O;
-  for(double* p: {d_chol, Loo, Lov, Lvv, G}) cudaFree(p);
   if(brc) return ctx->fail("cublasDgemm failed", 10);
   ctx->synthetic = false;
   return 0;
