@@ -29,3 +29,20 @@ def test_cholesky_truncation_reproduces_the_integrals_to_the_tolerance():
     assert nvec < eri.shape[0] ** 2 and np.abs(approx - eri).max() < 1e-7
     # 8-fold permutational symmetry of the two-electron integrals
     assert np.abs(eri - eri.transpose(1, 0, 2, 3)).max() < 1e-13 and np.abs(eri - eri.transpose(2, 3, 0, 1)).max() < 1e-13
+
+
+def test_ch4_triplet_uhf_reproduces_the_published_open_shell_triples_golden():
+    """ci/reference_output/ch4.def2-tzvp.ccsd_t.json (inputs/ci/ch4.json: UHF triplet, def2-TZVP with f functions, 6 alpha /
+    4 beta electrons, ccsdt_tilesize 28): SCF, CCSD, total_num_ops and the [T] / (T) corrections of the reference's own
+    open-shell CI run, from integrals, UHF and spin-orbital CCSD that share nothing with it, through the oracle with
+    is_restricted = false.  The reference stopped its CCSD at 1e-6; agreement is stated at 2e-8 Eh (observed 7e-9)."""
+    from oracle.oracle import Oracle
+    T, info = pv.solve_uhf(os.path.join(REF, "inputs/ci/ch4.json"), os.path.join(REF, "exachem/basis"), 3, verbose=False)
+    assert (info["nbf"], info["n_occ_alpha"], info["n_occ_beta"]) == (55, 6, 4)
+    assert abs(info["e_scf"] - (-39.81922867041884)) < 1e-9
+    assert abs(info["e_ccsd_corr"] - (-0.21543138440366036)) < 1e-7
+    orc = Oracle()
+    sp = orc.tiles(6, 4, 49, 51, 28)
+    assert orc.count_ops(sp, False) == 37432196256
+    e1, e2 = orc.run(sp, T, False)
+    assert abs(e1 - (-0.00802036907441595)) < 2e-8 and abs(e2 - (-0.007817304224704037)) < 2e-8

@@ -95,7 +95,20 @@ def _sph_from_cart(l):
         M[idx[(2, 0, 0)], 3], M[idx[(0, 2, 0)], 3] = 1.0, -1.0                                # xx-yy
         M[idx[(1, 1, 0)], 4] = 1.0                                                            # xy
         return M
-    raise NotImplementedError("pure functions beyond d are not needed for the reference's small inputs")
+    if l == 3:
+        M = np.zeros((10, 7))
+        def put(col, terms):
+            for pw_, c in terms:
+                M[idx[pw_], col] = c
+        put(0, [((0, 0, 3), 2.0), ((2, 0, 1), -3.0), ((0, 2, 1), -3.0)])          # z(2zz-3xx-3yy)
+        put(1, [((1, 0, 2), 4.0), ((3, 0, 0), -1.0), ((1, 2, 0), -1.0)])          # x(4zz-xx-yy)
+        put(2, [((0, 1, 2), 4.0), ((2, 1, 0), -1.0), ((0, 3, 0), -1.0)])          # y(4zz-xx-yy)
+        put(3, [((2, 0, 1), 1.0), ((0, 2, 1), -1.0)])                             # z(xx-yy)
+        put(4, [((1, 1, 1), 1.0)])                                                # xyz
+        put(5, [((3, 0, 0), 1.0), ((1, 2, 0), -3.0)])                             # x(xx-3yy)
+        put(6, [((2, 1, 0), 3.0), ((0, 3, 0), -1.0)])                             # y(3xx-yy)
+        return M
+    raise NotImplementedError("pure functions beyond f are not needed for the reference's small inputs")
 
 
 class Molecule:
