@@ -18,14 +18,17 @@ _u8p = C.POINTER(C.c_uint8)
 class Options(C.Structure):
     _fields_ = [("kernel", C.c_int32), ("sub", C.c_int32 * 3), ("stages", C.c_int32),
                 ("ctas_per_sm", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
-                ("overlap", C.c_int32), ("stagger", C.c_int32), ("verbose", C.c_int32), ("symmetry", C.c_int32)]
+                ("overlap", C.c_int32), ("stagger", C.c_int32), ("verbose", C.c_int32), ("symmetry", C.c_int32),
+                ("exec_tilesize", C.c_int32), ("prefetch_tasks", C.c_int32), ("block_budget_bytes", C.c_int64),
+                ("watchdog_ms", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class Stats(C.Structure):
     _fields_ = [("tasks_run", C.c_int64), ("kernel_launches", C.c_int64), ("counted_flops", C.c_double),
                 ("seconds_total", C.c_double), ("seconds_kernel", C.c_double),
                 ("seconds_staging", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("blocks_fetched", C.c_int64), ("evaluated_flops", C.c_double)]
+                ("blocks_fetched", C.c_int64), ("evaluated_flops", C.c_double), ("blocks_evicted", C.c_int64),
+                ("seconds_fetch", C.c_double), ("seconds_host_wait", C.c_double), ("executed_flops", C.c_double)]
 
 
 FETCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, _u32p, _dp, C.c_size_t)
@@ -49,6 +52,18 @@ SIGNATURES = {
     "ccsdt_put_block": (C.c_int, [C.c_void_p, C.c_int, _u32p, _dp]),
     "ccsdt_set_fetch": (C.c_int, [C.c_void_p, FETCH_FN, C.c_void_p]),
     "ccsdt_set_synthetic": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "ccsdt_clear_blocks": (C.c_int, [C.c_void_p]),
+    "ccsdt_release_cached": (C.c_int, []),
+    "ccsdt_exec_tiles": (C.c_int, [C.c_void_p, _i64p, _i32p, _i32p, C.c_int]),
+    "ccsdt_num_tasks": (C.c_int64, [C.c_void_p]),
+    "ccsdt_make_exec_tiles": (C.c_int, [C.c_int] * 4 + [_i64p, _i32p, C.c_int, _i64p, _i32p, _i32p, C.c_int]),
+    "ccsdt_split_request": (C.c_int64, [C.c_int] * 4 + [_i64p, _i32p, _i64p, _i32p, C.c_int, _u32p, _i64p, C.c_int64]),
+    "ccsdt_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "ccsdt_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "ccsdt_comm_allreduce": (C.c_int, [C.c_void_p, _dp]),
+    "ccsdt_comm_destroy": (C.c_int, [C.c_void_p]),
+    "ccsdt_task_counter_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_i64p)]),
+    "ccsdt_task_counter_close": (C.c_int, [_i64p, C.c_char_p, C.c_int]),
     "ccsdt_put_cholesky": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "ccsdt_set_task_counter": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ccsdt_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _dp, C.POINTER(Stats)]),

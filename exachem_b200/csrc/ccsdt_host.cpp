@@ -276,4 +276,92 @@ std::vector<int32_t> partition_tasks(const Space& sp, const std::vector<Task>& t
   return owner;
 }
 
+// ------------------------------------------------------------------------------------------------
+// execution tiling
+static void cut_block(int64_t n, int64_t target, int64_t gran, std::vector<int64_t>& out) {
+  if(n <= 0) return;
+  // ceil(n / target) tiles; the extent is dealt out in units of `gran` as evenly as possible (larger tiles first) and
+  // the last tile gives back the padding of the last unit: 195 at target 40 -> 40,40,40,40,35; 93 at 32 -> 32,32,29
+  const int64_t nt = (n + target - 1) / target, units = (n + gran - 1) / gran;
+  const int64_t base = units / nt, extra = units % nt;
+  int64_t       left = n;
+  for(int64_t i = 0; i < nt && left > 0; i++) {
+    const int64_t e = std::min(left, (base + (i < extra ? 1 : 0)) * gran);
+    if(e <= 0) continue; // fewer units than tiles
+    out.push_back(e);
+    left -= e;
+  }
+}
+
+Space make_exec_space(const Space& store, int target) {
+  const int nt = store.noab() + store.nvab();
+  int64_t   tmax = 0;
+  for(int t = 0; t < nt; t++) tmax = std::max(tmax, store.k_range[t]);
+  if(target < 0) {
+    // auto: keep a storage tiling the kernel already likes
+    bool keep = tmax >= 24;
+    for(int t = store.noab(); t < nt && keep; t++) {
+      const bool last_of_spin = t == nt - 1 || store.k_spin[t + 1] != store.k_spin[t];
+      if(!last_of_spin && store.k_range[t] % 8) keep = false;
+    }
+    if(keep) return store;
+    target = (int) std::max<int64_t>(40, (tmax + 7) / 8 * 8);
+  }
+  if(target == 0) return store;
+  const int64_t        tp = std::max(8, (target + 7) / 8 * 8), th = std::max(2, (target + 1) / 2 * 2);
+  std::vector<int64_t> kr;
+  std::vector<int32_t> ks;
+  int                  cnt[4] = {0, 0, 0, 0};
+  for(int g = 0; g < 4; g++) {
+    const bool particle = g >= 2;
+    int        tb, te;
+    int64_t    n;
+    store.spin_range(particle, g % 2 + 1, tb, te, n);
+    const size_t before = kr.size();
+    cut_block(n, particle ? tp : th, particle ? 8 : 2, kr);
+    cnt[g] = (int) (kr.size() - before);
+    for(int i = 0; i < cnt[g]; i++) ks.push_back(g % 2 + 1);
+  }
+  return make_space(cnt[0], cnt[1], cnt[2], cnt[3], kr.data(), ks.data(), store.evl.empty() ? nullptr : store.evl.data(),
+                    store.restricted);
+}
+
+bool same_tiling(const Space& a, const Space& b) {
+  return a.noa == b.noa && a.nob == b.nob && a.nva == b.nva && a.nvb == b.nvb && a.k_range == b.k_range;
+}
+
+std::vector<TilePiece> split_tile(const Space& exec, const Space& store, int exec_tile) {
+  std::vector<TilePiece> out;
+  const bool    particle = exec_tile >= exec.noab();
+  const int64_t lo = exec.k_offset[exec_tile], hi = lo + exec.k_range[exec_tile]; // spin-orbital numbers: both spaces
+  const int     sb = particle ? store.noab() : 0, se = particle ? store.noab() + store.nvab() : store.noab(); // order alike
+  // exec and store number the orbitals identically (occ a | occ b | virt a | virt b), but the occupied/virtual split
+  // is at k_offset[noab] in each: the same value, since both hold the same orbitals
+  for(int t = sb; t < se; t++) {
+    const int64_t a = std::max(lo, store.k_offset[t]), b = std::min(hi, store.k_offset[t] + store.k_range[t]);
+    if(a < b) out.push_back(TilePiece{t, a - store.k_offset[t], a - lo, b - a});
+  }
+  return out;
+}
+
+int canonical_block(int tensor, uint32_t bid[4], int perm[4]) {
+  for(int d = 0; d < 4; d++) perm[d] = d;
+  int  sign = 1;
+  auto order = [&](int i, int j, bool ascending) {
+    if(ascending ? bid[i] > bid[j] : bid[i] < bid[j]) {
+      std::swap(bid[i], bid[j]);
+      std::swap(perm[i], perm[j]);
+      sign = -sign;
+    }
+  };
+  switch(tensor) {
+    case 1: order(0, 1, true), order(2, 3, true); break;   // T2[a,b,i,j]
+    case 2: order(0, 1, false), order(2, 3, false); break; // v2ijab[i,j,a,b]: the reference asks {h_hi,h_lo,p_hi,p_lo}
+    case 3: order(0, 1, true); break;                      // v2ijka[i,j,k,a]
+    case 4: order(2, 3, true); break;                      // v2iabc[i,a,b,c]
+    default: break;                                        // T1
+  }
+  return sign;
+}
+
 } // namespace ccsdt

@@ -86,4 +86,33 @@ long double task_cost(const Space& sp, const Task& t, bool symmetry);
 std::vector<int32_t> partition_tasks(const Space& sp, const std::vector<Task>& tasks, int nranks,
                                      bool symmetry = true);
 
+// ---- execution tiling --------------------------------------------------------------------------
+// The STORAGE tiling is the caller's (setupMOIS: the block ids Tensor::get understands).  The EXECUTION tiling is the
+// one the task list, the panels and the kernel work on.  They coincide by default (per-task parity with the
+// reference); otherwise every spin block is re-cut into near-equal tiles whose extents are multiples of the CTA box
+// (8 for particles, 2 for holes) so that no task pads a ragged tile up to the box: ts 28 (caffeine, H2O) executes
+// 32^3 / 28^3 = x1.49 DMMAs per particle triple on its own tiles and x1.08 on execution tiles of 40.
+// target > 0: requested execution tile extent; target < 0 (auto): max(40, storage tile rounded up to 8), and the
+// storage tiling is kept as it is when all its particle tiles but the last of each spin block are multiples of 8.
+Space make_exec_space(const Space& store, int target);
+// true when a and b describe the same tiles
+bool  same_tiling(const Space& a, const Space& b);
+
+// One tensor dimension of an execution tile cut along the storage tiles it overlaps.
+struct TilePiece {
+  int32_t store_tile; // tile id in the storage space (global id: particle tiles include the noab offset)
+  int64_t store_off;  // first element inside the storage tile
+  int64_t exec_off;   // first element inside the execution tile
+  int64_t len;
+};
+// particle = the dimension is virtual; exec_tile / store_tile are global tile ids of their spaces
+std::vector<TilePiece> split_tile(const Space& exec, const Space& store, int exec_tile);
+
+// The blocks the reference requests are canonically ordered: T2{p_lo,p_hi,h_lo,h_hi},
+// v2ijka{h_lo,h_hi,h7,p}, v2iabc{h,p7,p_lo,p_hi}, v2ijab{h_hi,h_lo,p_hi,p_lo}.  A storage sub-block of a diagonal
+// execution block may come out in the other order; canonical_block swaps the offending pair(s) of `bid`, records the
+// dimension permutation (requested dim d is dim perm[d] of the canonical block) and returns the sign (-1)^swaps.
+// tensor ids as in include/ccsdt_b200.h.
+int canonical_block(int tensor, uint32_t bid[4], int perm[4]);
+
 } // namespace ccsdt

@@ -47,14 +47,25 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 }
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, uint32_t* error_flag, int tag) {
   // long suspend hint + back-off: a waiting warp (the producer, almost always) must not eat issue slots of
-  // the DMMA warps that share its scheduler
-  const long long t0 = clock64();
+  // the DMMA warps that share its scheduler.  The watchdog runs on %globaltimer (wall-clock nanoseconds, so a
+  // context that is time-sliced out by MPS, a second rank on the GPU or a debugger is not mistaken for a dead
+  // pipeline as quickly as with SM cycles) against the limit the host wrote behind the error word
+  // (options.watchdog_ms; 0 = never).
+  uint64_t limit = 0, t0 = 0;
+  if(error_flag) {
+    limit = (uint64_t) error_flag[1] | ((uint64_t) error_flag[2] << 32);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  }
   while(!mbar_try_wait_hint(bar, parity, 20000u)) {
     __nanosleep(100);
-    if(clock64() - t0 > 4000000000ll) { // ~2 s
-      if(error_flag) atomicExch(error_flag, 0xDEAD0000u | (uint32_t) tag);
-      __threadfence_system();
-      __trap();
+    if(limit) {
+      uint64_t t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if(t1 - t0 > limit) {
+        atomicExch(error_flag, 0xDEAD0000u | (uint32_t) tag);
+        __threadfence_system();
+        __trap();
+      }
     }
   }
 }

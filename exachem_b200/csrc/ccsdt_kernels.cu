@@ -985,8 +985,9 @@ cudaError_t probe_tma_swizzle(double* dump_host, int rows) {
   uint32_t* flag;
   cudaMalloc(&src, (size_t) rows * 16 * 8);
   cudaMalloc(&dump, (size_t) rows * 16 * 8);
-  cudaMalloc(&flag, 4);
-  cudaMemset(flag, 0, 4);
+  cudaMalloc(&flag, 16);
+  const uint32_t flag_init[4] = {0u, 2000000000u, 0u, 0u}; // error word, then the watchdog limit: 2 s of %globaltimer
+  cudaMemcpy(flag, flag_init, 16, cudaMemcpyHostToDevice);
   double* h = (double*) malloc((size_t) rows * 16 * 8);
   for(int i = 0; i < rows * 16; i++) h[i] = (double) i;
   cudaMemcpy(src, h, (size_t) rows * 16 * 8, cudaMemcpyHostToDevice);

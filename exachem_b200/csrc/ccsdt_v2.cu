@@ -1,0 +1,174 @@
+// V2 tensors from Cholesky vectors on the device (row f2 of SURVEY.md 8f).
+#include "ccsdt_ctx.hpp"
+
+#include <algorithm>
+#include <dlfcn.h>
+
+using namespace ccsdt;
+
+extern "C" {
+// =================================================================================================
+// V2 from Cholesky vectors (row f2 of SURVEY.md 8f): replaces setupV2Tensors
+// (exachem/cholesky/v2tensors.cpp:52-90, called at exachem/cc/ccsd_t/ccsd_t.cpp:168-193)
+//   v2ijab(h1,h2,p1,p2) = L(h1,p1,c) L(h2,p2,c) - L(h1,p2,c) L(h2,p1,c)      v2tensors.cpp:68-69
+//   v2ijka(h1,h2,h3,p1) = L(h1,h3,c) L(h2,p1,c) - L(h2,h3,c) L(h1,p1,c)      v2tensors.cpp:77-78
+//   v2iabc(h1,p1,p2,p3) = L(h1,p2,c) L(p1,p3,c) - L(h1,p3,c) L(p1,p2,c)      v2tensors.cpp:85-86
+// Each is one plain FP64 GEMM over the Cholesky index (cuBLAS, loaded on first use) followed by an
+// antisymmetrising gather; v2iabc is formed one occupied row at a time, so the GEMM scratch is V^3, not O V^3.
+// =================================================================================================
+} // extern "C"
+
+namespace {
+
+// rows (p in [p0,p0+np), q in [q0,q0+nq)) of chol[N][N][ncv] packed as out[(p,q)][ncv]
+__global__ void __launch_bounds__(256) pack_pairs_kernel(const double* __restrict__ chol, int64_t N, int64_t ncv, int64_t p0,
+                                                         int64_t np, int64_t q0, int64_t nq, double* __restrict__ out) {
+  const int64_t total = np * nq * ncv;
+  for(int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+    const int64_t c = e % ncv, pq = e / ncv, q = pq % nq, pp = pq / nq;
+    out[e]          = chol[((p0 + pp) * N + (q0 + q)) * ncv + c];
+  }
+}
+// v2ijab[h1,h2,p1,p2] from G[(h1,p1),(h2,p2)]  (G is OV x OV)
+__global__ void __launch_bounds__(256) v2ijab_kernel(const double* __restrict__ G, int64_t O, int64_t V, double* __restrict__ out) {
+  const int64_t total = O * O * V * V, OV = O * V;
+  for(int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+    int64_t       r  = e;
+    const int64_t p2 = r % V; r /= V;
+    const int64_t p1 = r % V; r /= V;
+    const int64_t h2 = r % O, h1 = r / O;
+    out[e] = G[(h1 * V + p1) * OV + h2 * V + p2] - G[(h1 * V + p2) * OV + h2 * V + p1];
+  }
+}
+// v2ijka[h1,h2,h3,p1] from G[(h1,h3),(h2,p1)]  (G is OO x OV)
+__global__ void __launch_bounds__(256) v2ijka_kernel(const double* __restrict__ G, int64_t O, int64_t V, double* __restrict__ out) {
+  const int64_t total = O * O * O * V, OV = O * V;
+  for(int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+    int64_t       r  = e;
+    const int64_t p1 = r % V; r /= V;
+    const int64_t h3 = r % O; r /= O;
+    const int64_t h2 = r % O, h1 = r / O;
+    out[e] = G[(h1 * O + h3) * OV + h2 * V + p1] - G[(h2 * O + h3) * OV + h1 * V + p1];
+  }
+}
+// one occupied row: v2iabc[h1,p1,p2,p3] from G[(p2),(p1,p3)]  (G is V x VV for this h1)
+__global__ void __launch_bounds__(256) v2iabc_row_kernel(const double* __restrict__ G, int64_t V, double* __restrict__ out) {
+  const int64_t total = V * V * V, VV = V * V;
+  for(int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+    int64_t       r  = e;
+    const int64_t p3 = r % V; r /= V;
+    const int64_t p2 = r % V, p1 = r / V;
+    out[e] = G[p2 * VV + p1 * V + p3] - G[p3 * VV + p1 * V + p2];
+  }
+}
+
+// the four cuBLAS entry points this file needs, resolved from libcublas.so.12 on first use
+struct Cublas {
+  void* lib = nullptr;
+  void* handle = nullptr;
+  int (*create)(void**) = nullptr;
+  int (*destroy)(void*) = nullptr;
+  int (*set_stream)(void*, cudaStream_t) = nullptr;
+  int (*dgemm)(void*, int, int, int, int, int, const double*, const double*, int, const double*, int, const double*, double*,
+               int) = nullptr;
+  std::string open() {
+    if(handle) return "";
+    for(const char* name: {"libcublas.so.12", "libcublas.so"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if(lib) break;
+    }
+    if(!lib) return std::string("cannot load libcublas: ") + dlerror();
+    create     = (int (*)(void**)) dlsym(lib, "cublasCreate_v2");
+    destroy    = (int (*)(void*)) dlsym(lib, "cublasDestroy_v2");
+    set_stream = (int (*)(void*, cudaStream_t)) dlsym(lib, "cublasSetStream_v2");
+    dgemm      = (decltype(dgemm)) dlsym(lib, "cublasDgemm_v2");
+    if(!create || !destroy || !set_stream || !dgemm) return "libcublas lacks cublasCreate/Destroy/SetStream/Dgemm";
+    if(create(&handle) != 0) return "cublasCreate failed";
+    return "";
+  }
+  // row-major C[m][n] = A[m][k] * B[n][k]^T
+  int abt(cudaStream_t st, int m, int n, int k, const double* A, const double* B, double* C) {
+    const double one = 1.0, zero = 0.0;
+    set_stream(handle, st);
+    return dgemm(handle, /*CUBLAS_OP_T*/ 1, /*CUBLAS_OP_N*/ 0, n, m, k, &one, B, k, A, k, &zero, C, n);
+  }
+  ~Cublas() {
+    if(handle && destroy) destroy(handle);
+  }
+};
+Cublas g_cublas;
+
+inline unsigned grid_for(int64_t n) { return (unsigned) std::min<int64_t>((n + 255) / 256, 148 * 16); }
+
+int dense_alloc(ccsdt_ctx* ctx, int tensor, size_t n) {
+  if(ctx->dense[tensor] && ctx->dense_elems[tensor] != n) {
+    CK(cudaFree(ctx->dense[tensor]));
+    ctx->dense[tensor] = nullptr;
+  }
+  if(!ctx->dense[tensor]) {
+    CK(cudaMalloc(&ctx->dense[tensor], n * 8));
+    ctx->dense_elems[tensor] = n;
+  }
+  ctx->dense_sparse_ok[tensor] = false; // written in full by the caller (ccsdt_put_cholesky)
+  return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int ccsdt_put_cholesky(ccsdt_ctx* ctx, const double* host_chol, int64_t ncv) {
+  if(!ctx || !host_chol || ncv <= 0) return 1;
+  if(!ctx->have_space) return ctx->fail("ccsdt_set_space must be called first");
+  cudaSetDevice(ctx->device);
+  const std::string cerr = g_cublas.open();
+  if(!cerr.empty()) return ctx->fail(cerr, 10);
+  const int64_t O = ctx->sp.n_occ(), V = ctx->sp.n_virt(), N = O + V;
+  if(O * V * ncv > 0x7fffffffll || V * V > 0x7fffffffll) return ctx->fail("ccsdt_put_cholesky: GEMM dimension exceeds int32", 10);
+  CK(cudaStreamSynchronize(ctx->s_compute));
+  CK(cudaStreamSynchronize(ctx->s_compute2));
+  cudaStream_t st = ctx->s_stage;
+  double *d_chol = nullptr, *Loo = nullptr, *Lov = nullptr, *Lvv = nullptr, *G = nullptr;
+  struct Scratch { // the temporaries are released on every way out (the CK macro returns on failure)
+    double** p[5];
+    ~Scratch() {
+      for(double** q: p)
+        if(*q) cudaFree(*q);
+    }
+  } scratch{{&d_chol, &Loo, &Lov, &Lvv, &G}};
+  const size_t nchol = (size_t) N * N * ncv;
+  CK(cudaMalloc(&d_chol, nchol * 8));
+  CK(cudaMemcpyAsync(d_chol, host_chol, nchol * 8, cudaMemcpyHostToDevice, st));
+  ctx->pending_h2d += (int64_t) nchol * 8;
+  CK(cudaMalloc(&Loo, (size_t) O * O * ncv * 8));
+  CK(cudaMalloc(&Lov, (size_t) O * V * ncv * 8));
+  CK(cudaMalloc(&Lvv, (size_t) V * V * ncv * 8));
+  pack_pairs_kernel<<<grid_for(O * O * ncv), 256, 0, st>>>(d_chol, N, ncv, 0, O, 0, O, Loo);
+  pack_pairs_kernel<<<grid_for(O * V * ncv), 256, 0, st>>>(d_chol, N, ncv, 0, O, O, V, Lov);
+  pack_pairs_kernel<<<grid_for(V * V * ncv), 256, 0, st>>>(d_chol, N, ncv, O, V, O, V, Lvv);
+  CK(cudaGetLastError());
+  // scratch for the largest product: (OV x OV), (OO x OV) or one row of (V x VV)
+  const size_t gmax = std::max({(size_t) O * V * O * V, (size_t) O * O * O * V, (size_t) V * V * V});
+  CK(cudaMalloc(&G, gmax * 8));
+  if(int rc = dense_alloc(ctx, CCSDT_V_IJAB, (size_t) O * O * V * V)) return rc;
+  if(int rc = dense_alloc(ctx, CCSDT_V_IJKA, (size_t) O * O * O * V)) return rc;
+  if(int rc = dense_alloc(ctx, CCSDT_V_IABC, (size_t) O * V * V * V)) return rc;
+  int brc = 0;
+  brc |= g_cublas.abt(st, (int) (O * V), (int) (O * V), (int) ncv, Lov, Lov, G);
+  v2ijab_kernel<<<grid_for(O * O * V * V), 256, 0, st>>>(G, O, V, ctx->dense[CCSDT_V_IJAB]);
+  brc |= g_cublas.abt(st, (int) (O * O), (int) (O * V), (int) ncv, Loo, Lov, G);
+  v2ijka_kernel<<<grid_for(O * O * O * V), 256, 0, st>>>(G, O, V, ctx->dense[CCSDT_V_IJKA]);
+  for(int64_t h1 = 0; h1 < O; h1++) {
+    brc |= g_cublas.abt(st, (int) V, (int) (V * V), (int) ncv, Lov + h1 * V * ncv, Lvv, G);
+    v2iabc_row_kernel<<<grid_for(V * V * V), 256, 0, st>>>(G, V, ctx->dense[CCSDT_V_IABC] + h1 * V * V * V);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  ctx->stats.kernel_launches += 5 + 2 * O;
+  if(brc) return ctx->fail("cublasDgemm failed", 10);
+  ctx->synthetic = false;
+  return 0;
+}
+
+
+} // extern "C"

@@ -216,6 +216,32 @@ class Context:
     def set_synthetic(self, seed: int):
         self._ck(self.L.ccsdt_set_synthetic(self.h, seed))
 
+    def clear_blocks(self):
+        """drop every fetched block from the HBM block store: the next run starts cold, like a fresh execute"""
+        self._ck(self.L.ccsdt_clear_blocks(self.h))
+
+    def exec_space(self) -> TiledSpace:
+        """the execution tiling in force (options exec_tilesize); task ids of run / run_tasks index ITS task list"""
+        cap = 4096
+        kr, ks, cnt = np.zeros(cap, np.int64), np.zeros(cap, np.int32), np.zeros(4, np.int32)
+        n = self.L.ccsdt_exec_tiles(self.h, _p(kr, _lib._i64p), _p(ks, _lib._i32p), _p(cnt, _lib._i32p), cap)
+        if n <= 0:
+            raise CcsdtError("ccsdt_exec_tiles failed (no space set?)")
+        return TiledSpace(int(cnt[0]), int(cnt[1]), int(cnt[2]), int(cnt[3]), kr[:n].copy(), ks[:n].copy())
+
+    def num_tasks(self) -> int:
+        return int(self.L.ccsdt_num_tasks(self.h))
+
+    # ---- the one collective, inside the C ABI (NCCL) ----
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.L.ccsdt_comm_init(self.h, buf, rank, nranks))
+
+    def comm_allreduce(self, e1: float, e2: float):
+        e = np.array([e1, e2], np.float64)
+        self._ck(self.L.ccsdt_comm_allreduce(self.h, _p(e, _lib._dp)))
+        return float(e[0]), float(e[1])
+
     def set_task_counter(self, address: int | None):
         """address of a process-shared int64 (see multigpu.SharedTaskCounter); None = static split."""
         self._ck(self.L.ccsdt_set_task_counter(self.h, C.c_void_p(address) if address else None))

@@ -8,10 +8,19 @@
 // libccsdt_b200.so on the GPU; there is no CPU path here.
 //
 // Contract kept from the reference:
-//   * one host rank drives one GPU (the rank's current CUDA device, as TAMM bound it);
-//   * the returned energies are rank PARTIALS -- the caller sums them over ranks
-//     (ccsd_t.cpp:262-263); the library's static cost-balanced split replaces the GA atomic counter
-//     (reference lines 169-172, 381, 456);
+//   * one host rank drives one GPU (the rank's current CUDA device, as TAMM bound it).  ONE rank per GPU: the
+//     fused kernel sizes its grid for the whole device, and several ranks time-slicing one GPU only add latency;
+//   * the returned energies are rank PARTIALS -- the caller sums them over ranks (ccsd_t.cpp:262-263).
+//     With CCSDT_B200_INTERNAL_ALLREDUCE defined the library's own ncclAllReduce combines them
+//     (ccsdt_comm_*; the unique id travels through ec.pg().broadcast) and the total is returned on rank 0
+//     and 0.0 elsewhere, so that the caller's reduce still yields the total;
+//   * task hand-out across ranks: on one node (ec.nnodes() == 1) the ranks share an atomic counter in POSIX
+//     shared memory and claim tasks longest-first (the role of AtomicCounterGA, reference lines 169-172, 381,
+//     456); across nodes, or with CCSDT_B200_DYNAMIC=0, the static cost-balanced split of the library;
+//   * execution tiling: by default (CCSDT_B200_EXEC_TILESIZE unset or -1) the library re-cuts ragged or tiny
+//     tiles (ts 28 -> execution tiles of 40, see ccsdt_options.exec_tilesize); blocks are still requested from
+//     Tensor::get in the caller's tiling and only canonically ordered ones, like the reference.  0 keeps the
+//     caller's tiles (the reference's task list, task for task);
 //   * the six LRUCache arguments are accepted and ignored: the library's HBM block store caches
 //     every fetched block for the whole call (the reference caches sorted copies on the host);
 //   * hf_ccsd_energy, seq_h3b and tilesize_opt are unused, as in the reference body;
@@ -27,7 +36,9 @@
 
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
 #include <string>
+#include <unistd.h>
 #include <tuple>
 #include <type_traits>
 #include <vector>
@@ -35,6 +46,10 @@
 #ifndef CCSDT_B200_TERMINATE
 // real TAMM provides tamm::tamm_terminate(std::string); a test shim may define this macro instead
 #define CCSDT_B200_TERMINATE(msg) tamm_terminate(msg)
+#endif
+#ifndef CCSDT_B200_SINGLE_NODE
+// all ranks of ec.pg() share one node (and its POSIX shared memory): TAMM's ExecutionContext knows
+#define CCSDT_B200_SINGLE_NODE(ec) ((ec).nnodes() == 1)
 #endif
 
 namespace ccsdt_b200_detail {
@@ -116,8 +131,15 @@ public:
                                          bool is_restricted, long double& total_num_ops,
                                          bool seq_h3b = false);
 
-  // statistics of the last execute() on this object (not part of the reference interface)
+  // ---- not part of the reference interface ----
+  // statistics of the last execute() on this object
   ccsdt_stats last_stats{};
+  // when non-empty, execute() runs only these kernel tasks (indices into the execution task list) instead of the
+  // whole job: benchmarks and tests of problems whose whole job takes hours
+  std::vector<int64_t> task_subset;
+  // library options applied on top of the defaults (rank / nranks are always taken from ec)
+  bool          have_options = false;
+  ccsdt_options options{};
 };
 
 template<typename T>
@@ -147,12 +169,16 @@ std::tuple<T, T, double, double> CCSD_T_Fused_Driver<T>::execute(
     }
   };
 
+  const int     rank = (int) ec.pg().rank().value(), nranks = (int) ec.pg().size().value();
   ccsdt_options opt;
   ccsdt_default_options(&opt);
-  opt.rank   = (int32_t) ec.pg().rank().value();
-  opt.nranks = (int32_t) ec.pg().size().value();
+  opt.exec_tilesize = -1; // auto: re-cut ragged / tiny tiles; totals do not depend on it
+  if(have_options) opt = options;
+  opt.rank   = (int32_t) rank;
+  opt.nranks = (int32_t) nranks;
   // CCSDT_B200_SYMMETRY=0 evaluates every element of every task as the reference does (see ccsdt_options.symmetry)
   if(const char* e = std::getenv("CCSDT_B200_SYMMETRY")) opt.symmetry = std::atoi(e) != 0;
+  if(const char* e = std::getenv("CCSDT_B200_EXEC_TILESIZE")) opt.exec_tilesize = std::atoi(e);
   check(ccsdt_set_options(ctx, &opt));
   check(ccsdt_set_space(ctx, s.noa, s.nob, s.nva, s.nvb, s.k_range.data(), s.k_spin.data(), evl.data(),
                         is_restricted ? 1 : 0));
@@ -165,8 +191,50 @@ std::tuple<T, T, double, double> CCSD_T_Fused_Driver<T>::execute(
   user.tensor[CCSDT_V_IABC] = &d_v2.v2iabc;
   check(ccsdt_set_fetch(ctx, &fetch_block<T>, &user));
 
+  // dynamic hand-out among the ranks of one node: rank 0 creates the shared counter, the others attach after a
+  // barrier (reference: AtomicCounterGA allocate / fetch_add / deallocate, lines 169-172, 456, 541)
+  int64_t*    counter = nullptr;
+  std::string counter_name;
+  bool        dynamic = nranks > 1 && CCSDT_B200_SINGLE_NODE(ec);
+  if(const char* e = std::getenv("CCSDT_B200_DYNAMIC")) dynamic = dynamic && std::atoi(e) != 0;
+  if(dynamic) {
+    const char* key = std::getenv("CCSDT_B200_COUNTER_KEY");
+    counter_name    = "/ccsdt_b200_" + std::to_string((long) getuid()) + "_" + (key ? key : "0");
+    if(rank == 0 && ccsdt_task_counter_open(counter_name.c_str(), 1, &counter)) {
+      ccsdt_destroy(ctx);
+      CCSDT_B200_TERMINATE("[CCSD(T) B200] cannot create the shared task counter " + counter_name);
+    }
+    ec.pg().barrier();
+    if(rank != 0 && ccsdt_task_counter_open(counter_name.c_str(), 0, &counter)) {
+      ccsdt_destroy(ctx);
+      CCSDT_B200_TERMINATE("[CCSD(T) B200] cannot attach to the shared task counter " + counter_name);
+    }
+    check(ccsdt_set_task_counter(ctx, counter));
+  }
+
   double energies[2] = {0.0, 0.0};
-  check(ccsdt_run(ctx, 0, -1, energies, nullptr, &last_stats));
+  if(task_subset.empty()) check(ccsdt_run(ctx, 0, -1, energies, nullptr, &last_stats));
+  else check(ccsdt_run_tasks(ctx, task_subset.data(), (int64_t) task_subset.size(), energies, nullptr, &last_stats));
+
+#if defined(CCSDT_B200_INTERNAL_ALLREDUCE)
+  if(nranks > 1) {
+    // the one collective, inside the library: ncclAllReduce of {E[T], E(T)}
+    unsigned char id[128];
+    if(rank == 0 && ccsdt_comm_unique_id(id)) {
+      ccsdt_destroy(ctx);
+      CCSDT_B200_TERMINATE("[CCSD(T) B200] ncclGetUniqueId failed (is libnccl.so.2 loadable?)");
+    }
+    ec.pg().broadcast(id, sizeof(id), 0);
+    check(ccsdt_comm_init(ctx, id, rank, nranks));
+    check(ccsdt_comm_allreduce(ctx, energies));
+    if(rank != 0) energies[0] = energies[1] = 0.0; // the caller reduces what execute returns (ccsd_t.cpp:262-263)
+  }
+#endif
+  if(dynamic) {
+    check(ccsdt_set_task_counter(ctx, nullptr));
+    ec.pg().barrier(); // every rank has drawn its last task
+    ccsdt_task_counter_close(counter, counter_name.c_str(), rank == 0 ? 1 : 0);
+  }
   ccsdt_destroy(ctx);
   ec.pg().barrier(); // the reference ends its timed region with a barrier (line 536)
 

@@ -84,6 +84,21 @@ typedef struct ccsdt_options {
                             permutation multiplicity (t3 is antisymmetric in same-spin indices, so d*d/D and
                             d*(d+s)/D are symmetric; the reference evaluates every element and lets `factor`
                             undo the over-count, ccsd_t_fused_driver.hpp:387-395); 0 = evaluate every box */
+  int32_t exec_tilesize; /* execution tiling (the tiles the task list, the panels and the kernel work on):
+                            0 (default) = the caller's tiles, i.e. the reference's task list and per-task energies;
+                            > 0 = re-cut every spin block into near-equal tiles of about this extent, multiples of the CTA
+                            box (8 particles / 2 holes), so that ragged tiles (ts 28: 28 -> 32 per particle index, x1.49
+                            executed DMMAs) and tiny tiles (ts 16) cost nothing; blocks are still fetched in the caller's
+                            tiling and cut or merged by the panel build; -1 = auto (re-cut only when the caller's particle
+                            tiles are not multiples of 8 or are smaller than 24).  Task ids of ccsdt_run / ccsdt_run_tasks
+                            then index the execution task list (ccsdt_exec_tiles + ccsdt_enumerate); totals are unchanged */
+  int32_t prefetch_tasks; /* static hand-out + fetch callback: blocks of up to this many upcoming tasks are fetched while
+                            the host would otherwise wait for the GPU; 0 = default (4), -1 = off */
+  int64_t block_budget_bytes; /* HBM the block store may hold before it evicts least-recently-used blocks;
+                            0 = what is free after the panel pools are allocated, minus a reserve */
+  int32_t watchdog_ms;   /* a pipeline wait inside the fused kernel that lasts longer than this traps (reported as a CUDA
+                            error) instead of hanging the GPU; 0 = default (20 000 ms of %globaltimer), -1 = never */
+  int32_t reserved_;
 } ccsdt_options;
 
 typedef struct ccsdt_stats {
@@ -97,13 +112,23 @@ typedef struct ccsdt_stats {
   int64_t blocks_fetched;     /* fetch-callback invocations */
   double  evaluated_flops;    /* counted_flops x (CTA boxes evaluated / CTA boxes of the tile): what the fused kernel
                                  had to execute after the symmetry reduction (== counted_flops with symmetry = 0) */
+  int64_t blocks_evicted;     /* blocks the LRU dropped from the HBM block store during the run */
+  double  seconds_fetch;      /* host time spent inside the fetch callback (the caller's Tensor::get) */
+  double  seconds_host_wait;  /* host time blocked on the GPU (buffer reuse, ring space, final synchronisation) */
+  double  executed_flops;     /* flops of the DMMAs the fused kernel issued for the evaluated boxes: evaluated_flops
+                                 plus the padding of ragged tiles up to the CTA box and of K up to 4 */
 } ccsdt_stats;
 
 /* delivers one UNSORTED row-major block, i.e. what Tensor<T>::get(bid, buf) returns */
 typedef int (*ccsdt_fetch_fn)(void* user, int tensor, const uint32_t bid[4], double* dst, size_t n);
 
+/* ccsdt_destroy parks the context's device resources (streams, panel pools, the pinned fetch ring, the private memory
+ * pool) for the next ccsdt_create on the same device of this process -- CCSD_T_Fused_Driver::execute creates and
+ * destroys a context per call, and on a 0.2 s job allocation would otherwise cost as much as the work.
+ * ccsdt_release_cached frees what is parked; CCSDT_B200_CACHE=0 in the environment disables parking. */
 CCSDT_API int         ccsdt_create(ccsdt_ctx** out, int device); /* device < 0: the calling thread's current CUDA device */
 CCSDT_API int         ccsdt_destroy(ccsdt_ctx* ctx);
+CCSDT_API int         ccsdt_release_cached(void);
 CCSDT_API const char* ccsdt_last_error(const ccsdt_ctx* ctx); /* ctx may be NULL: error of the last failed create */
 CCSDT_API int         ccsdt_default_options(ccsdt_options* opt);
 CCSDT_API int         ccsdt_set_options(ccsdt_ctx* ctx, const ccsdt_options* opt);
@@ -132,6 +157,20 @@ CCSDT_API int     ccsdt_box_weight(int sym, const int32_t box[6]);
 /* problem definition */
 CCSDT_API int ccsdt_set_space(ccsdt_ctx* ctx, int noa, int nob, int nva, int nvb, const int64_t* k_range,
                     const int32_t* k_spin, const double* evl, int is_restricted);
+/* the execution tiling in force (== the tiles of ccsdt_set_space unless options.exec_tilesize re-cut them); returns the
+ * number of tiles, or minus that number when cap is too small.  counts = tiles per (occ a, occ b, virt a, virt b) */
+CCSDT_API int     ccsdt_exec_tiles(const ccsdt_ctx* ctx, int64_t* k_range, int32_t* k_spin, int32_t counts[4], int cap);
+CCSDT_API int64_t ccsdt_num_tasks(const ccsdt_ctx* ctx); /* kernel tasks of the execution task list */
+/* host-only: the execution tiling ccsdt_set_space + options.exec_tilesize = target would produce */
+CCSDT_API int     ccsdt_make_exec_tiles(int noa, int nob, int nva, int nvb, const int64_t* k_range, const int32_t* k_spin,
+                                        int target, int64_t* out_range, int32_t* out_spin, int32_t counts[4], int cap);
+/* host-only (CPU tests of the re-tiling logic): the canonical storage blocks one execution-tile block request
+ * exec_bid of `tensor` is cut into.  22 int64 per piece: bid[4] of the canonical storage block, sign (+1/-1 of the
+ * canonicalisation), perm[4] (requested dim d is dim perm[d] of the canonical block), store_off[4], exec_off[4], len[4]
+ * (per requested dim), elems of the storage block.  Returns the number of pieces. */
+CCSDT_API int64_t ccsdt_split_request(int noa, int nob, int nva, int nvb, const int64_t* store_range, const int32_t* store_spin,
+                                      const int64_t* exec_range, const int32_t* exec_counts, int tensor,
+                                      const uint32_t exec_bid[4], int64_t* pieces /* 22 per piece */, int64_t cap);
 
 /* operand supply (choose one per tensor).  ccsdt_put_dense copies only the spin-conserving blocks of the dense host array
  * (T1: s_a = s_i; four-index tensors: s_0 + s_1 = s_2 + s_3 -- the only blocks any task reads and the only ones the
@@ -143,12 +182,29 @@ CCSDT_API int ccsdt_put_dense(ccsdt_ctx* ctx, int tensor, const double* host_den
 CCSDT_API int ccsdt_put_dense_async(ccsdt_ctx* ctx, int tensor, const double* host_dense);
 CCSDT_API int ccsdt_put_block(ccsdt_ctx* ctx, int tensor, const uint32_t bid[4], const double* host_block);
 CCSDT_API int ccsdt_set_fetch(ccsdt_ctx* ctx, ccsdt_fetch_fn fn, void* user);
+/* drops every fetched block from the HBM block store (blocks given by ccsdt_put_block stay): the next run starts cold,
+ * as a fresh CCSD_T_Fused_Driver::execute does */
+CCSDT_API int ccsdt_clear_blocks(ccsdt_ctx* ctx);
 CCSDT_API int ccsdt_set_synthetic(ccsdt_ctx* ctx, uint64_t seed); /* procedural tensors generated on the device */
 /* The three V2 tensors formed on the device from Cholesky vectors: host_chol[N][N][ncv] over all spin orbitals in tile
  * order (occupied first), what ExaChem holds as cholVpr.  Replaces setupV2Tensors (exachem/cholesky/v2tensors.cpp:52-90,
  * called at exachem/cc/ccsd_t/ccsd_t.cpp:168-193): one cuBLAS DGEMM over the Cholesky index per tensor (libcublas is
  * loaded on first use) plus an antisymmetrising gather.  Equivalent to ccsdt_put_dense on v2ijab, v2ijka and v2iabc. */
 CCSDT_API int ccsdt_put_cholesky(ccsdt_ctx* ctx, const double* host_chol, int64_t ncv);
+
+/* The one collective of the path, inside the C ABI: ncclAllReduce(sum) of {E[T], E(T)} over all ranks, on the context's
+ * GPU (replaces the two ec.pg().reduce calls of exachem/cc/ccsd_t/ccsd_t.cpp:262-263).  libnccl.so.2 is loaded on first
+ * use.  ccsdt_comm_unique_id fills 128 bytes on one rank (ncclGetUniqueId); the caller broadcasts them (MPI_Bcast, a file,
+ * a torch store) and every rank calls ccsdt_comm_init.  After ccsdt_comm_allreduce every rank holds the totals: a caller
+ * that reduces again (ExaChem does) must use the value of rank 0 only -- the C++ adapter returns 0 on the other ranks. */
+CCSDT_API int ccsdt_comm_unique_id(void* id128);
+CCSDT_API int ccsdt_comm_init(ccsdt_ctx* ctx, const void* id128, int rank, int nranks);
+CCSDT_API int ccsdt_comm_allreduce(ccsdt_ctx* ctx, double energies[2]);
+CCSDT_API int ccsdt_comm_destroy(ccsdt_ctx* ctx);
+/* A process-shared int64 task counter in POSIX shared memory (shm_open + mmap) for ccsdt_set_task_counter: the rank with
+ * create = 1 makes and zeroes it, the others attach after a barrier; ccsdt_task_counter_close(ptr, name, unlink). */
+CCSDT_API int ccsdt_task_counter_open(const char* name, int create, int64_t** counter);
+CCSDT_API int ccsdt_task_counter_close(int64_t* counter, const char* name, int unlink_it);
 
 /* Dynamic task hand-out across ranks: `counter` points to an int64 in memory shared by all ranks of the
  * node (POSIX/SysV shared memory, an MPI shared window, ...), zeroed before every ccsdt_run by one rank

@@ -27,6 +27,11 @@
 #include <tuple>
 #include <vector>
 
+#include <cstring>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
 namespace tamm {
 
 using Index       = uint32_t;
@@ -134,20 +139,76 @@ private:
 };
 
 // ec.pg().rank().value(), ec.pg().barrier()  (ccsd_t_fused_driver.hpp:99,536)
+// Single rank by default.  With TAMM_SHIM_SIZE > 1 in the environment (and TAMM_SHIM_RANK, TAMM_SHIM_KEY) the ranks
+// are separate processes of one node that meet in a POSIX shared-memory segment "/tamm_shim_<key>" (4 KiB, created
+// and zeroed by the launcher before the ranks start): a sense-reversing barrier, a broadcast buffer and one slot per
+// rank for a sum -- enough for the multi-rank tests of the drop-in header.
 struct RankValue {
   int64_t v;
   int64_t value() const { return v; }
 };
 class ProcGroup {
 public:
-  RankValue rank() const { return {0}; }
-  RankValue size() const { return {1}; }
-  void      barrier() const {}
+  ProcGroup() {
+    const char *r = std::getenv("TAMM_SHIM_RANK"), *n = std::getenv("TAMM_SHIM_SIZE"), *k = std::getenv("TAMM_SHIM_KEY");
+    if(!r || !n || std::atoi(n) <= 1) return;
+    rank_ = std::atoi(r), size_ = std::atoi(n);
+    const std::string name = std::string("/tamm_shim_") + (k ? k : "0");
+    const int         fd   = shm_open(name.c_str(), O_RDWR, 0600);
+    if(fd < 0) {
+      std::cerr << "shim ProcGroup: cannot open " << name << std::endl;
+      std::abort();
+    }
+    mem_ = (unsigned char*) mmap(nullptr, 4096, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if(mem_ == (unsigned char*) MAP_FAILED) std::abort();
+  }
+  RankValue rank() const { return {rank_}; }
+  RankValue size() const { return {size_}; }
+  void      barrier() const {
+    if(size_ <= 1) return;
+    int64_t *     count = (int64_t*) mem_, *gen = (int64_t*) (mem_ + 64);
+    const int64_t g = __atomic_load_n(gen, __ATOMIC_ACQUIRE);
+    if(__atomic_add_fetch(count, 1, __ATOMIC_ACQ_REL) == size_) {
+      __atomic_store_n(count, 0, __ATOMIC_RELAXED);
+      __atomic_add_fetch(gen, 1, __ATOMIC_ACQ_REL);
+    }
+    else
+      while(__atomic_load_n(gen, __ATOMIC_ACQUIRE) == g) usleep(20);
+  }
+  // TAMM: pg.broadcast(buf, count, root)
+  template<typename T>
+  void broadcast(T* buf, size_t count, int root) const {
+    if(size_ <= 1) return;
+    const size_t bytes = count * sizeof(T);
+    if(bytes > 2048) std::abort();
+    if(rank_ == root) std::memcpy(mem_ + 1024, buf, bytes);
+    barrier();
+    if(rank_ != root) std::memcpy(buf, mem_ + 1024, bytes);
+    barrier();
+  }
+  // sum over ranks, result on every rank (stands in for the caller's ec.pg().reduce of ccsd_t.cpp:262-263)
+  double allreduce_sum(double v) const {
+    if(size_ <= 1) return v;
+    double* slots = (double*) (mem_ + 3072);
+    slots[rank_]  = v;
+    barrier();
+    double s = 0;
+    for(int64_t i = 0; i < size_; i++) s += slots[i];
+    barrier();
+    return s;
+  }
+
+private:
+  int64_t        rank_ = 0, size_ = 1;
+  unsigned char* mem_  = nullptr;
 };
 class ExecutionContext {
 public:
   ProcGroup&       pg() { return pg_; }
   const ProcGroup& pg() const { return pg_; }
+  int              nnodes() const { return 1; } // the stand-in's ranks always share one node
+  int              ppn() const { return (int) pg_.size().value(); }
 
 private:
   ProcGroup pg_;
