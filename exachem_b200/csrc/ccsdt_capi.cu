@@ -642,6 +642,13 @@ int collect_timing(ccsdt_ctx* ctx, StageBuf& b) {
   ctx->kernel_busy_until = std::max(ctx->kernel_busy_until, (double) ms1);
   CK(cudaEventElapsedTime(&ms, b.g0, b.g1));
   ctx->stats.seconds_staging += ms * 1e-3;
+  if(b.trace_slot >= 0 && b.trace_slot < (int64_t) ctx->trace.size()) {
+    TraceRow& r = ctx->trace[b.trace_slot];
+    float     g0 = 0, g1 = 0;
+    CK(cudaEventElapsedTime(&g0, ctx->ev_base, b.g0));
+    CK(cudaEventElapsedTime(&g1, ctx->ev_base, b.g1));
+    r.gather0 = g0, r.gather1 = g1, r.k0 = ms0, r.k1 = ms1;
+  }
   b.timing_pending = false;
   return 0;
 }
@@ -661,6 +668,54 @@ void missing_blocks(ccsdt_ctx* ctx, const Task& t, std::vector<SrcPiece>& out, s
     [](double*, const int64_t*, const int*) { return 0; });
 }
 
+// Execution order of a rank's tasks when the operands come through the fetch callback.  The host thread and the GPU
+// form a two-stage flow shop: stage 1 pulls a task's missing blocks through the callback (the caller's Tensor::get, on
+// this thread), stage 2 is the GPU.  Units are the particle-tile triples (p4b,p5b,p6b): the tasks of one triple share
+// their v2iabc and most of their T2 blocks, so they run back to back and those blocks are fetched (and stay resident)
+// once per triple.  Units run in ascending order of the bytes they need, in octaves (units of similar size keep their
+// canonical order, hence the block reuse between neighbouring triples): the GPU starts after a SMALL fetch, and the
+// data of the big units arrive under the kernels of the smaller ones before them (measured on the benzene shape: the
+// 180 MB of the first mixed-spin task cost 32 ms of idle GPU at the head of a 215 ms job when it came first, 9 ms with
+// this order).  Per-task energies are summed in canonical order, so the result does not depend on the order.
+void order_for_fetch(ccsdt_ctx* ctx, std::vector<int64_t>& order) {
+  struct Unit {
+    std::array<int32_t, 3> key;
+    std::vector<int64_t>   tasks;
+    double                 bytes = 0, flops = 0;
+  };
+  std::map<std::array<int32_t, 3>, size_t> index;
+  std::vector<Unit>                        units;
+  std::vector<SrcPiece>                    pieces, scratch;
+  for(int64_t id: order) {
+    const Task&                  t = ctx->tasks[id];
+    const std::array<int32_t, 3> key{t.t[3], t.t[4], t.t[5]};
+    auto                         it = index.find(key);
+    if(it == index.end()) {
+      it = index.emplace(key, units.size()).first;
+      units.push_back(Unit{key, {}, 0, 0});
+    }
+    units[it->second].tasks.push_back(id);
+    units[it->second].flops += (double) task_cost(ctx->sp, t, ctx->opt.symmetry != 0);
+  }
+  for(Unit& u: units) {
+    std::map<BlockKey, size_t> seen;
+    for(int64_t id: u.tasks) {
+      pieces.clear();
+      missing_blocks(ctx, ctx->tasks[id], pieces, scratch);
+      for(const SrcPiece& p: pieces) seen[p.key] = p.elems * 8;
+    }
+    for(auto& kv: seen) u.bytes += (double) kv.second;
+  }
+  auto octave = [](double bytes) {
+    int o = 0;
+    for(double x = bytes; x >= 2.0; x *= 0.5) o++;
+    return o;
+  };
+  std::stable_sort(units.begin(), units.end(), [&](const Unit& x, const Unit& y) { return octave(x.bytes) < octave(y.bytes); });
+  order.clear();
+  for(const Unit& u: units) order.insert(order.end(), u.tasks.begin(), u.tasks.end());
+}
+
 } // namespace
 
 static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool use_global_split, double energies[2],
@@ -668,6 +723,7 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
   cudaSetDevice(ctx->device);
   const double t0 = now_s();
   ctx->stats           = ccsdt_stats{};
+  ctx->trace.clear();
   ctx->stats.h2d_bytes = ctx->pending_h2d; // uploads (ccsdt_put_*) since the previous run belong to this one
   ctx->pending_h2d     = 0;
   energies[0] = energies[1] = 0.0;
@@ -699,17 +755,6 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
       if(own[k] == ctx->opt.rank) order.push_back(ids[k]);
   }
   const bool fetching = ctx->fetch && !ctx->synthetic;
-  if(!ctx->task_counter && fetching) {
-    // blocks come through the callback: run the tasks of one particle-tile triple back to back -- they share their
-    // v2iabc and most of their T2 blocks, which then stay resident (and are fetched) once per triple.  The result
-    // does not depend on the execution order: per-task energies are summed in canonical order below.
-    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-      const Task &x = ctx->tasks[a], &y = ctx->tasks[b];
-      for(int i = 3; i < 6; i++)
-        if(x.t[i] != y.t[i]) return x.t[i] < y.t[i];
-      return false;
-    });
-  }
   {
     // uploads in flight: the tasks that only need the all-alpha blocks (the first to arrive) go first; per-task energies
     // are summed in canonical order whatever the execution order
@@ -732,6 +777,7 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
   if(!order.empty()) {
     if(int rc = ensure_pools(ctx)) return rc;
     if(int rc = update_block_budget(ctx)) return rc;
+    if(!ctx->task_counter && fetching) order_for_fetch(ctx, order);
     const int64_t cap = (int64_t) order.size();
     if(cap > ctx->task_energy_cap) {
       if(ctx->d_task_energy) CK(cudaFree(ctx->d_task_energy));
@@ -753,11 +799,13 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
     ctx->kernel_busy_until = 0.0;
 
     // Prefetch (static hand-out, blocks through the callback): while the host would only wait for the GPU to
-    // release a staging buffer, it pulls the blocks of the next tasks into HBM -- the callback (the caller's
-    // Tensor::get) runs on this thread, its copies travel on s_fetch.  Blocks of future tasks carry their future
+    // release a staging buffer, it pulls the blocks of the tasks to come into HBM -- the callback (the caller's
+    // Tensor::get) runs on this thread, its copies travel on s_fetch.  It runs as far ahead as the block budget
+    // allows (options.prefetch_tasks bounds it in tasks): the order of order_for_fetch puts the fetch-heavy tasks
+    // last, and their blocks arrive under the long kernels before them.  Blocks of future tasks carry their future
     // clock, so the LRU does not take them back before they are used.
     const int64_t lookahead = (!ctx->task_counter && fetching && ctx->opt.prefetch_tasks >= 0)
-                                ? (ctx->opt.prefetch_tasks > 0 ? ctx->opt.prefetch_tasks : 4) : 0;
+                                ? (ctx->opt.prefetch_tasks > 0 ? ctx->opt.prefetch_tasks : ((int64_t) 1 << 40)) : 0;
     int64_t               pf_task = 0;      // next entry of `order` whose blocks have not been listed
     std::vector<SrcPiece> pf_queue, scratch;
     size_t                pf_pos   = 0;
@@ -776,8 +824,15 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
       }
       const SrcPiece& p = pf_queue[pf_pos++];
       if(ctx->blocks.count(p.key)) return 0;
-      // a prefetch must not push out blocks of the tasks in flight: it only uses free budget
-      if(ctx->block_budget && ctx->block_bytes + p.elems * 8 > ctx->block_budget) return 1;
+      // a prefetch never pushes out blocks of the tasks in flight or of tasks still to come (the LRU only gives up
+      // blocks whose last reader has passed); when that does not make room it pauses until tasks have retired
+      if(ctx->block_budget && ctx->block_bytes + p.elems * 8 > ctx->block_budget) {
+        if(int rc = evict_stale(ctx, p.elems * 8)) return -rc;
+        if(ctx->block_bytes + p.elems * 8 > ctx->block_budget) {
+          pf_pos--;
+          return 1;
+        }
+      }
       BlockRef ref;
       if(int rc = resolve_block(ctx, p.key, p.elems, pf_clock, ref)) return -rc;
       return 0;
@@ -799,8 +854,14 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
         if(int rc = collect_timing(ctx, b)) return rc;
       }
       CK(cudaStreamWaitEvent(ctx->s_stage, b.done, 0));
+      const double tr0 = now_s() - t0, tf0 = ctx->stats.seconds_fetch;
       if(int rc = stage_task(ctx, b, ctx->tasks[ti], descs, scratch)) return rc;
       if(int rc = launch_task(ctx, b, j)) return rc;
+      b.trace_slot = -1;
+      if(ctx->opt.verbose >= 2) {
+        b.trace_slot = (int64_t) ctx->trace.size();
+        ctx->trace.push_back(TraceRow{ti, tr0, now_s() - t0, ctx->stats.seconds_fetch - tf0, 0, 0, 0, 0});
+      }
       const double ops = (double) task_ops(ctx->sp, ctx->tasks[ti]);
       ctx->stats.counted_flops += ops;
       ctx->stats.evaluated_flops += ops * (ctx->opt.kernel == CCSDT_KERNEL_DMMA ? b.eval_fraction : 1.0);
@@ -846,6 +907,16 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
   for(int tn = 0; tn < 5; tn++) ctx->upload_pending[tn] = false;
   ctx->stats.seconds_total = now_s() - t0;
   if(stats_out) *stats_out = ctx->stats;
+  if(ctx->opt.verbose >= 2) {
+    fprintf(stderr, "[ccsdt trace] run of %zu tasks, %.3f ms total; per task: id | host stage begin..end ms (fetch ms) | gather ms | kernel k0..k1 ms\n",
+            ctx->trace.size(), ctx->stats.seconds_total * 1e3);
+    for(const TraceRow& r: ctx->trace) {
+      const Task& t = ctx->tasks[r.task];
+      fprintf(stderr, "[ccsdt trace] %5lld (%d,%d,%d|%d,%d,%d) | %8.3f..%8.3f (%7.3f) | %8.3f..%8.3f | %8.3f..%8.3f\n", (long long) r.task,
+              t.t[0], t.t[1], t.t[2], t.t[3], t.t[4], t.t[5], r.host_begin * 1e3, r.host_staged * 1e3, r.fetch_s * 1e3, r.gather0, r.gather1,
+              r.k0, r.k1);
+    }
+  }
   return 0;
 }
 

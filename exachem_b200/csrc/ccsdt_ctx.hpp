@@ -71,6 +71,15 @@ struct StageBuf {
   size_t       smem = 0;
   double       eval_fraction = 1.0; // boxes evaluated / boxes of the tile (symmetry)
   cudaStream_t cs = nullptr;        // compute stream of this buffer (see run_task_list)
+  int64_t      trace_slot = -1;     // options.verbose >= 2: row of the run's trace this buffer's task fills
+};
+
+// one row of the per-task trace (options.verbose >= 2, printed to stderr at the end of the run)
+struct TraceRow {
+  int64_t task;
+  double  host_begin, host_staged; // seconds after the start of the run: staging began / kernels were enqueued
+  double  fetch_s;                 // host time inside the fetch callback while staging this task (prefetch excluded)
+  double  gather0, gather1, k0, k1; // ms after ev_base on the GPU time line
 };
 
 // one enabled source of a task's panels, in execution-tile block ids
@@ -131,6 +140,7 @@ struct ccsdt_ctx {
   void*           encode_fn = nullptr;
   int64_t*        task_counter = nullptr; // process-shared dynamic task counter (NULL = static split)
   ccsdt_stats     stats{};
+  std::vector<ccsdt::TraceRow> trace;
   int64_t         pending_h2d = 0; // bytes uploaded by ccsdt_put_* since the last run
   // asynchronous dense uploads (ccsdt_put_dense_async): the all-alpha blocks of every tensor travel on s_copy_a,
   // the other spin patterns on s_copy_b; tasks whose six tiles are all alpha only wait for the first
@@ -172,6 +182,7 @@ void    store_destroy(ccsdt_ctx* ctx);
 void    free_operands(ccsdt_ctx* ctx);                          // dense tensors and every block
 int     clear_blocks(ccsdt_ctx* ctx, bool keep_pinned);
 int     update_block_budget(ccsdt_ctx* ctx);
+int     evict_stale(ccsdt_ctx* ctx, size_t bytes); // LRU: make room for `bytes` within the budget, as far as the rule allows
 // Storage pieces of one source: calls fn(key, elems, piece) for every storage block the execution-tile source
 // overlaps.  piece.src_off / stride are filled by resolve (fn may ignore them).
 struct SrcPiece {

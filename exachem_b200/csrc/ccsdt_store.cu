@@ -209,6 +209,8 @@ static int evict(ccsdt_ctx* ctx, size_t bytes, bool force, bool* evicted_any) {
   return 0;
 }
 
+int evict_stale(ccsdt_ctx* ctx, size_t bytes) { return evict(ctx, bytes, false, nullptr); }
+
 int resolve_block(ccsdt_ctx* ctx, const BlockKey& key, size_t elems, int64_t for_clock, BlockRef& out) {
   auto it = ctx->blocks.find(key);
   if(it == ctx->blocks.end()) {

@@ -93,7 +93,8 @@ typedef struct ccsdt_options {
                             tiles are not multiples of 8 or are smaller than 24).  Task ids of ccsdt_run / ccsdt_run_tasks
                             then index the execution task list (ccsdt_exec_tiles + ccsdt_enumerate); totals are unchanged */
   int32_t prefetch_tasks; /* static hand-out + fetch callback: blocks of up to this many upcoming tasks are fetched while
-                            the host would otherwise wait for the GPU; 0 = default (4), -1 = off */
+                            the host would otherwise wait for the GPU; 0 = default (as far ahead as the block budget
+                            allows), -1 = off */
   int64_t block_budget_bytes; /* HBM the block store may hold before it evicts least-recently-used blocks;
                             0 = what is free after the panel pools are allocated, minus a reserve */
   int32_t watchdog_ms;   /* a pipeline wait inside the fused kernel that lasts longer than this traps (reported as a CUDA

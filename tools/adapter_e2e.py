@@ -33,7 +33,7 @@ for tid, d in dims.items():
 evl = syn.Orbitals(no, no, nv, nv).orbital_energies()
 kr, ks = np.ascontiguousarray(sp.k_range, np.int64), np.ascontiguousarray(sp.k_spin, np.int32)
 out, gets, ops, st = np.zeros(4), np.zeros(5, np.int64), C.c_longdouble(0), _lib.Stats()
-for rep in range(int(os.environ.get('ADAPTER_REPS', '2'))):
+for rep in range(int(os.environ.get('ADAPTER_REPS', '4'))):
     t0 = time.perf_counter()
     rc = H.adapter_ccsdt_execute(sp.noa, sp.nob, sp.nva, sp.nvb, kr.ctypes.data_as(_lib._i64p), ks.ctypes.data_as(_lib._i32p),
                                  evl.ctypes.data_as(_lib._dp), *[host[t].ctypes.data_as(_lib._dp) for t in range(5)], 1, ts,
@@ -42,7 +42,8 @@ for rep in range(int(os.environ.get('ADAPTER_REPS', '2'))):
     assert rc == 0, H.adapter_last_error()
     print(f"adapter execute #{rep}: {dt:.3f} s wall, {float(ops.value) / dt / 1e12:.2f} TFLOP/s counted end to end; "
           f"ccsdt_run {st.seconds_total:.3f} s, kernel {st.seconds_kernel:.3f} s, staging {st.seconds_staging:.3f} s, {st.blocks_fetched} blocks / "
-          f"{st.h2d_bytes / 1e9:.2f} GB fetched through Tensor::get, E[T] {out[0]:.12e} E(T) {out[1]:.12e}")
+          f"{st.h2d_bytes / 1e9:.2f} GB fetched through Tensor::get ({st.seconds_fetch:.3f} s inside the callback, host waited {st.seconds_host_wait:.3f} s "
+          f"for the GPU), E[T] {out[0]:.12e} E(T) {out[1]:.12e}")
 ctx = drv.Context(0)
 ctx.set_space(sp, evl, True)
 ctx.set_synthetic(1234)
