@@ -28,7 +28,8 @@ class Stats(C.Structure):
                 ("seconds_total", C.c_double), ("seconds_kernel", C.c_double),
                 ("seconds_staging", C.c_double), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("blocks_fetched", C.c_int64), ("evaluated_flops", C.c_double), ("blocks_evicted", C.c_int64),
-                ("seconds_fetch", C.c_double), ("seconds_host_wait", C.c_double), ("executed_flops", C.c_double)]
+                ("seconds_fetch", C.c_double), ("seconds_host_wait", C.c_double), ("executed_flops", C.c_double),
+                ("blocks_from_peers", C.c_int64), ("peer_bytes", C.c_int64)]
 
 
 FETCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, _u32p, _dp, C.c_size_t)
@@ -62,6 +63,8 @@ SIGNATURES = {
     "ccsdt_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "ccsdt_comm_allreduce": (C.c_int, [C.c_void_p, _dp]),
     "ccsdt_comm_destroy": (C.c_int, [C.c_void_p]),
+    "ccsdt_share_attach": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    "ccsdt_share_detach": (C.c_int, [C.c_void_p]),
     "ccsdt_task_counter_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_i64p)]),
     "ccsdt_task_counter_close": (C.c_int, [_i64p, C.c_char_p, C.c_int]),
     "ccsdt_put_cholesky": (C.c_int, [C.c_void_p, _dp, C.c_int64]),

@@ -775,9 +775,15 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
   if(per_task) std::fill(per_task, per_task + 2 * nids, 0.0);
 
   if(!order.empty()) {
+    const double m0 = now_s();
     if(int rc = ensure_pools(ctx)) return rc;
+    const double m1 = now_s();
     if(int rc = update_block_budget(ctx)) return rc;
+    const double m2 = now_s();
     if(!ctx->task_counter && fetching) order_for_fetch(ctx, order);
+    if(ctx->opt.verbose >= 2)
+      fprintf(stderr, "[ccsdt trace] before the loop: hand-out %.3f ms, pools %.3f ms, budget %.3f ms, order %.3f ms\n", (m0 - t0) * 1e3,
+              (m1 - m0) * 1e3, (m2 - m1) * 1e3, (now_s() - m2) * 1e3);
     const int64_t cap = (int64_t) order.size();
     if(cap > ctx->task_energy_cap) {
       if(ctx->d_task_energy) CK(cudaFree(ctx->d_task_energy));
@@ -904,6 +910,7 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
   CK(cudaStreamSynchronize(ctx->s_copy_a));
   CK(cudaStreamSynchronize(ctx->s_copy_b));
   CK(cudaStreamSynchronize(ctx->s_fetch));
+  share_poll(ctx, true); // every block this rank fetched for the node is published, every peer copy accounted for
   for(int tn = 0; tn < 5; tn++) ctx->upload_pending[tn] = false;
   ctx->stats.seconds_total = now_s() - t0;
   if(stats_out) *stats_out = ctx->stats;
@@ -941,6 +948,7 @@ static void sync_streams(ccsdt_ctx* ctx) {
 static void real_destroy(ccsdt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   sync_streams(ctx);
+  share_detach(ctx);
   comm_destroy(ctx);
   free_pools(ctx);
   store_destroy(ctx);
@@ -1064,6 +1072,7 @@ int ccsdt_destroy(ccsdt_ctx* ctx) {
   if(cache) {
     // park: the logical state goes, the device resources (streams, events, panel pools, pinned ring, memory pool,
     // box lists) stay for the next ccsdt_create on this device
+    share_detach(ctx);
     comm_destroy(ctx);
     free_operands(ctx);
     ccsdt_default_options(&ctx->opt);

@@ -40,6 +40,8 @@ struct BlockEntry {
   int64_t last_use = 0;     // use_clock of the last task that reads it (a prefetched block carries its FUTURE clock)
   bool    pinned   = false; // supplied by ccsdt_put_block: cannot be fetched again, never evicted
   bool    pooled   = false; // allocated from the context's private memory pool (fetch path)
+  int     slab     = -1;    // >= 0: carved from slab `slab` of the node-shared store (ccsdt_share.cu) at `offset`
+  size_t  offset   = 0;
 };
 
 // which index kind ('o'/'v') each dimension of a tensor has
@@ -50,6 +52,8 @@ struct RingSeg {
   size_t      begin, end;
   cudaEvent_t ev;
 };
+
+struct ShareState;
 
 struct StageBuf {
   PoolGeom     geom{};
@@ -153,6 +157,8 @@ struct ccsdt_ctx {
     int32_t  n   = 0;
   };
   std::map<std::array<int, 19>, BoxList> box_lists;
+  // node-shared block directory (ccsdt_share.cu); NULL = private store
+  ccsdt::ShareState* share = nullptr;
   // the one collective (ccsdt_comm.cu)
   void* nccl_comm = nullptr;
   double* d_allreduce = nullptr;
@@ -201,6 +207,15 @@ int  resolve_block(ccsdt_ctx* ctx, const BlockKey& key, size_t elems, int64_t fo
 int  resolve_dense(ccsdt_ctx* ctx, int tensor, const uint32_t exec_bid[4], BlockRef& out);
 // records ev_fetched after the copies issued so far and makes `st` wait for it
 int  fetch_fence(ccsdt_ctx* ctx, cudaStream_t st);
+
+// ---- ccsdt_share.cu ----
+int    share_acquire(ccsdt_ctx* ctx, const BlockKey& key, size_t bytes, double** dev, int* slab, size_t* offset, void** entry);
+int    share_publish_after(ccsdt_ctx* ctx, void* entry, cudaStream_t st);
+bool   share_release(ccsdt_ctx* ctx, const BlockKey& key, BlockEntry& be, bool wait);
+void   share_free(ccsdt_ctx* ctx, int slab, size_t offset, size_t bytes);
+void   share_poll(ccsdt_ctx* ctx, bool wait);
+void   share_detach(ccsdt_ctx* ctx);
+size_t share_unused_bytes(const ccsdt_ctx* ctx);
 
 // ---- ccsdt_comm.cu ----
 void comm_destroy(ccsdt_ctx* ctx);

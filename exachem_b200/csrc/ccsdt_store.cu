@@ -83,11 +83,19 @@ void store_destroy(ccsdt_ctx* ctx) {
   ctx->ev_fetched = nullptr, ctx->s_fetch = nullptr;
 }
 
-static void release_block(ccsdt_ctx* ctx, BlockEntry& e) {
+// false: the block lives in the node-shared store and a peer is still copying it (only with wait = false)
+static bool release_block(ccsdt_ctx* ctx, const BlockKey& key, BlockEntry& e, bool wait) {
   // the last reader of a block is a panel build on s_stage: the release is ordered behind it
-  if(e.pooled) cudaFreeAsync(e.dev, ctx->s_stage);
+  if(e.slab >= 0) {
+    if(!share_release(ctx, key, e, wait)) return false;
+    // the region may be handed out again at once: the next copy into it (on s_fetch) waits for the panel builds queued so far
+    cudaEventRecord(ctx->ev_fetched, ctx->s_stage);
+    cudaStreamWaitEvent(ctx->s_fetch, ctx->ev_fetched, 0);
+  }
+  else if(e.pooled) cudaFreeAsync(e.dev, ctx->s_stage);
   else cudaFree(e.dev);
   ctx->block_bytes -= e.bytes;
+  return true;
 }
 
 int clear_blocks(ccsdt_ctx* ctx, bool keep_pinned) {
@@ -97,7 +105,7 @@ int clear_blocks(ccsdt_ctx* ctx, bool keep_pinned) {
       ++it;
       continue;
     }
-    release_block(ctx, it->second);
+    release_block(ctx, it->first, it->second, true);
     it = ctx->blocks.erase(it);
   }
   ctx->fetch_dirty = false;
@@ -113,6 +121,7 @@ void free_operands(ccsdt_ctx* ctx) {
     ctx->upload_pending[t]  = false;
   }
   clear_blocks(ctx, false);
+  share_poll(ctx, true);
   ctx->block_bytes = 0;
 }
 
@@ -131,7 +140,7 @@ int update_block_budget(ccsdt_ctx* ctx) {
     cudaMemPoolGetAttribute(ctx->block_pool, cudaMemPoolAttrUsedMemCurrent, &used);
   }
   const size_t reserve = std::max<size_t>((size_t) 2 << 30, total_b / 32);
-  const size_t avail   = free_b + (size_t) (reserved - used) + ctx->block_bytes;
+  const size_t avail   = free_b + (size_t) (reserved - used) + share_unused_bytes(ctx) + ctx->block_bytes;
   ctx->block_budget    = avail > reserve ? avail - reserve : avail / 2;
   return 0;
 }
@@ -190,6 +199,7 @@ static int ring_alloc(ccsdt_ctx* ctx, size_t bytes, uint8_t** out, size_t* begin
 // evicts least-recently-used blocks until `bytes` more fit the budget (or, with force, at least one block goes)
 static int evict(ccsdt_ctx* ctx, size_t bytes, bool force, bool* evicted_any) {
   if(evicted_any) *evicted_any = false;
+  std::vector<const BlockKey*> busy; // shared blocks a peer is copying right now: not this time
   while(force || (ctx->block_budget && ctx->block_bytes + bytes > ctx->block_budget)) {
     auto victim = ctx->blocks.end();
     for(auto jt = ctx->blocks.begin(); jt != ctx->blocks.end(); ++jt) {
@@ -197,10 +207,14 @@ static int evict(ccsdt_ctx* ctx, size_t bytes, bool force, bool* evicted_any) {
       // the task being staged (use_clock) and the one in flight (use_clock - 1) keep their blocks; prefetched blocks
       // carry a future clock
       if(e.pinned || e.last_use + 2 > ctx->use_clock) continue;
+      if(std::find(busy.begin(), busy.end(), &jt->first) != busy.end()) continue;
       if(victim == ctx->blocks.end() || e.last_use < victim->second.last_use) victim = jt;
     }
     if(victim == ctx->blocks.end()) break;
-    release_block(ctx, victim->second);
+    if(!release_block(ctx, victim->first, victim->second, false)) {
+      busy.push_back(&victim->first);
+      continue;
+    }
     ctx->blocks.erase(victim);
     ctx->stats.blocks_evicted++;
     if(evicted_any) *evicted_any = true;
@@ -221,21 +235,39 @@ int resolve_block(ccsdt_ctx* ctx, const BlockKey& key, size_t elems, int64_t for
     const size_t bytes = elems * 8;
     if(int rc = evict(ctx, bytes, false, nullptr)) return rc;
     double* dev = nullptr;
+    int     slab = -1;
+    size_t  slab_off = 0;
+    void*   dir_entry = nullptr; // node-shared store: the directory entry to publish once the upload has landed
+    bool    from_peer = false;
     for(int attempt = 0;; attempt++) {
-      cudaError_t e = cudaMallocFromPoolAsync((void**) &dev, bytes, ctx->block_pool, ctx->s_fetch);
-      if(e == cudaSuccess) break;
-      cudaGetLastError();
+      cudaError_t e = cudaSuccess;
+      if(ctx->share) {
+        const int rc = share_acquire(ctx, key, bytes, &dev, &slab, &slab_off, &dir_entry);
+        if(rc > 1) return rc;
+        from_peer = rc == 1;
+        if(rc >= 0) break;
+        e = cudaErrorMemoryAllocation;
+      }
+      else {
+        e = cudaMallocFromPoolAsync((void**) &dev, bytes, ctx->block_pool, ctx->s_fetch);
+        if(e == cudaSuccess) break;
+        cudaGetLastError();
+      }
       if(e != cudaErrorMemoryAllocation || attempt >= 64)
         return ctx->fail(std::string("block store allocation failed: ") + cudaGetErrorString(e), 2);
       // the budget was optimistic (another allocator took the memory): make room and retry
       bool any = false;
       if(int rc = evict(ctx, bytes, true, &any)) return rc;
-      if(!any) {
-        if(attempt > 0) return ctx->fail("out of device memory for the block store and nothing left to evict", 2);
-        CK(cudaStreamSynchronize(ctx->s_stage)); // pending releases
-      }
-      else CK(cudaStreamSynchronize(ctx->s_stage));
+      if(!any && attempt > 0) return ctx->fail("out of device memory for the block store and nothing left to evict", 2);
+      CK(cudaStreamSynchronize(ctx->s_stage)); // pending releases
     }
+    if(from_peer) { // the copy from the owner's HBM is on its way on s_fetch
+      ctx->block_bytes += bytes;
+      BlockEntry be;
+      be.dev = dev, be.bytes = bytes, be.last_use = for_clock, be.slab = slab, be.offset = slab_off;
+      it = ctx->blocks.emplace(key, be).first;
+    }
+    else {
     uint8_t* host  = nullptr;
     size_t   begin = 0;
     if(int rc = ring_alloc(ctx, bytes, &host, &begin)) return rc;
@@ -257,8 +289,10 @@ int resolve_block(ccsdt_ctx* ctx, const BlockKey& key, size_t elems, int64_t for
     ctx->stats.blocks_fetched++;
     ctx->block_bytes += bytes;
     BlockEntry be;
-    be.dev = dev, be.bytes = bytes, be.last_use = for_clock, be.pooled = true;
+    be.dev = dev, be.bytes = bytes, be.last_use = for_clock, be.pooled = slab < 0, be.slab = slab, be.offset = slab_off;
     it = ctx->blocks.emplace(key, be).first;
+    if(int rc = share_publish_after(ctx, dir_entry, ctx->s_fetch)) return rc;
+    }
   }
   it->second.last_use = std::max(it->second.last_use, for_clock);
   // row-major strides of the storage block

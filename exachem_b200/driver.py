@@ -232,6 +232,13 @@ class Context:
     def num_tasks(self) -> int:
         return int(self.L.ccsdt_num_tasks(self.h))
 
+    def share_attach(self, name: str, local_rank: int, local_ranks: int, create: bool):
+        """node-shared block store: blocks fetched by one rank of the node are read from its HBM by the others"""
+        self._ck(self.L.ccsdt_share_attach(self.h, name.encode(), local_rank, local_ranks, int(create)))
+
+    def share_detach(self):
+        self._ck(self.L.ccsdt_share_detach(self.h))
+
     # ---- the one collective, inside the C ABI (NCCL) ----
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
         buf = C.create_string_buffer(bytes(unique_id), 128)

@@ -16,7 +16,9 @@
 //     and 0.0 elsewhere, so that the caller's reduce still yields the total;
 //   * task hand-out across ranks: on one node (ec.nnodes() == 1) the ranks share an atomic counter in POSIX
 //     shared memory and claim tasks longest-first (the role of AtomicCounterGA, reference lines 169-172, 381,
-//     456); across nodes, or with CCSDT_B200_DYNAMIC=0, the static cost-balanced split of the library;
+//     456), and a block directory through which a block pulled from Tensor::get by one rank is read from that
+//     rank's HBM by the others (ccsdt_share_attach); across nodes, or with CCSDT_B200_DYNAMIC=0, the static
+//     cost-balanced split of the library and private block stores;
 //   * execution tiling: by default (CCSDT_B200_EXEC_TILESIZE unset or -1) the library re-cuts ragged or tiny
 //     tiles (ts 28 -> execution tiles of 40, see ccsdt_options.exec_tilesize); blocks are still requested from
 //     Tensor::get in the caller's tiling and only canonically ordered ones, like the reference.  0 keeps the
@@ -211,6 +213,16 @@ std::tuple<T, T, double, double> CCSD_T_Fused_Driver<T>::execute(
       CCSDT_B200_TERMINATE("[CCSD(T) B200] cannot attach to the shared task counter " + counter_name);
     }
     check(ccsdt_set_task_counter(ctx, counter));
+    // ... and the node-shared block store: a block is fetched through Tensor::get by ONE rank of the node and read from
+    // its HBM by the others (CCSDT_B200_SHARE=0 keeps every rank's store private)
+    bool share = true;
+    if(const char* e = std::getenv("CCSDT_B200_SHARE")) share = std::atoi(e) != 0;
+    if(share) {
+      const std::string dir = "/ccsdt_b200_dir_" + std::to_string((long) getuid()) + "_" + (key ? key : "0");
+      if(rank == 0) check(ccsdt_share_attach(ctx, dir.c_str(), rank, nranks, 1));
+      ec.pg().barrier();
+      if(rank != 0) check(ccsdt_share_attach(ctx, dir.c_str(), rank, nranks, 0));
+    }
   }
 
   double energies[2] = {0.0, 0.0};

@@ -118,6 +118,8 @@ typedef struct ccsdt_stats {
   double  seconds_host_wait;  /* host time blocked on the GPU (buffer reuse, ring space, final synchronisation) */
   double  executed_flops;     /* flops of the DMMAs the fused kernel issued for the evaluated boxes: evaluated_flops
                                  plus the padding of ragged tiles up to the CTA box and of K up to 4 */
+  int64_t blocks_from_peers;  /* blocks copied from another rank's HBM through the node-shared directory (ccsdt_share_attach) */
+  int64_t peer_bytes;         /* ... and their bytes (device to device over NVLink; not counted in h2d_bytes) */
 } ccsdt_stats;
 
 /* delivers one UNSORTED row-major block, i.e. what Tensor<T>::get(bid, buf) returns */
@@ -189,8 +191,8 @@ CCSDT_API int ccsdt_clear_blocks(ccsdt_ctx* ctx);
 CCSDT_API int ccsdt_set_synthetic(ccsdt_ctx* ctx, uint64_t seed); /* procedural tensors generated on the device */
 /* The three V2 tensors formed on the device from Cholesky vectors: host_chol[N][N][ncv] over all spin orbitals in tile
  * order (occupied first), what ExaChem holds as cholVpr.  Replaces setupV2Tensors (exachem/cholesky/v2tensors.cpp:52-90,
- * called at exachem/cc/ccsd_t/ccsd_t.cpp:168-193): one cuBLAS DGEMM over the Cholesky index per tensor (libcublas is
- * loaded on first use) plus an antisymmetrising gather.  Equivalent to ccsdt_put_dense on v2ijab, v2ijka and v2iabc. */
+ * called at exachem/cc/ccsd_t/ccsd_t.cpp:168-193): one FP64 DMMA GEMM over the Cholesky index per tensor (hand-written,
+ * csrc/ccsdt_v2.cu; no library call) plus an antisymmetrising gather.  Equivalent to ccsdt_put_dense on v2ijab, v2ijka and v2iabc. */
 CCSDT_API int ccsdt_put_cholesky(ccsdt_ctx* ctx, const double* host_chol, int64_t ncv);
 
 /* The one collective of the path, inside the C ABI: ncclAllReduce(sum) of {E[T], E(T)} over all ranks, on the context's
@@ -206,6 +208,15 @@ CCSDT_API int ccsdt_comm_destroy(ccsdt_ctx* ctx);
  * create = 1 makes and zeroes it, the others attach after a barrier; ccsdt_task_counter_close(ptr, name, unlink). */
 CCSDT_API int ccsdt_task_counter_open(const char* name, int create, int64_t** counter);
 CCSDT_API int ccsdt_task_counter_close(int64_t* counter, const char* name, int unlink_it);
+
+/* Node-shared block store (placement): the ranks of one node (one process per GPU) attach to a directory in
+ * POSIX shared memory `name`; a block is then pulled through the fetch callback by ONE rank of the node and copied from that
+ * rank's HBM by the others (CUDA IPC mapping, device-to-device over NVLink / NVSwitch) -- host-to-device traffic of the node
+ * is about that of a single rank, whatever the hand-out.  The rank with create = 1 makes the segment, the others attach
+ * after a barrier; ccsdt_share_detach (also called by ccsdt_destroy) is collective among the attached ranks.  Applies to
+ * blocks that arrive through ccsdt_set_fetch. */
+CCSDT_API int ccsdt_share_attach(ccsdt_ctx* ctx, const char* name, int local_rank, int local_ranks, int create);
+CCSDT_API int ccsdt_share_detach(ccsdt_ctx* ctx);
 
 /* Dynamic task hand-out across ranks: `counter` points to an int64 in memory shared by all ranks of the
  * node (POSIX/SysV shared memory, an MPI shared window, ...), zeroed before every ccsdt_run by one rank

@@ -4,12 +4,13 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * this file's library.  The product (exachem_b200/csrc) never links, imports or calls it.
  *
- * Parity is PINNED: tests/test_oracle_vs_ref.py compares every function here against the
- * reference's own code compiled unmodified (oracle/_ref/libccsdt_ref.so, see oracle/ref_driver.cpp)
- * -- task lists and exec tables bit-exact, energies bit-exact (same operation order, same compiler
- * flags) -- and tests/test_oracle_golden.py checks the six integer known-answer `total_num_ops`
- * values held by the reference's CI goldens (ci/reference_output/ *.ccsd_t.json) plus the fixtures in
- * tests/golden/ generated from the reference library.
+ * Parity is PINNED: tests/test_oracle.py compares every function here against the reference's own
+ * code compiled unmodified (oracle/_ref/libccsdt_ref.so, see oracle/ref_driver.cpp) -- task lists and
+ * exec tables bit-exact, energies bit-exact (same operation order, same compiler flags) -- and checks
+ * the six integer known-answer `total_num_ops` values held by the reference's CI goldens
+ * (ci/reference_output/ *.ccsd_t.json) plus the fixtures in tests/golden/ generated from the reference
+ * library (tests/golden/make_golden.py); tests/test_molecules.py and tests/test_provider.py add the
+ * reference's published [T] / (T) energies (butanol2, CH4 UHF) on amplitudes from tools/provider.
  *
  * All paths below are relative to /root/reference/exachem/.  Written from scratch in plain C99; the
  * reference is C++ templates over TAMM tensors.

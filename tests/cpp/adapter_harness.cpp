@@ -248,6 +248,39 @@ adapter_table_execute(void* h, const int32_t counts[4], int is_restricted, int t
   }
 }
 
+// host-only self-test of the multi-rank plumbing the drop-in header relies on (no GPU): the ranks are separate
+// processes (TAMM_SHIM_RANK / _SIZE / _KEY).  They meet in ec.pg() (barrier, broadcast), share the library's task counter
+// (ccsdt_task_counter_open) exactly as CCSD_T_Fused_Driver::execute does, and claim `n` tickets with atomic fetch-adds.
+// out[0] = tickets this rank claimed, out[1] = their sum, out[2] = sum over ranks of out[0], out[3] = of out[1],
+// out[4] = the value rank 0 broadcast.
+__attribute__((visibility("default"))) int adapter_multirank_selftest(int64_t n, const char* counter_name, int64_t* out) {
+  try {
+    ExecutionContext ec;
+    const int        rank = (int) ec.pg().rank().value();
+    int64_t*         counter = nullptr;
+    if(rank == 0 && ccsdt_task_counter_open(counter_name, 1, &counter)) throw std::runtime_error("counter create failed");
+    ec.pg().barrier();
+    if(rank != 0 && ccsdt_task_counter_open(counter_name, 0, &counter)) throw std::runtime_error("counter attach failed");
+    int64_t mine = 0, sum = 0;
+    for(;;) {
+      const int64_t k = __atomic_fetch_add(counter, (int64_t) 1, __ATOMIC_RELAXED);
+      if(k >= n) break;
+      mine++, sum += k;
+    }
+    int64_t magic = rank == 0 ? 0x5eed1234 : 0;
+    ec.pg().broadcast(&magic, 1, 0);
+    out[0] = mine, out[1] = sum, out[4] = magic;
+    out[2] = (int64_t) ec.pg().allreduce_sum((double) mine);
+    out[3] = (int64_t) ec.pg().allreduce_sum((double) sum);
+    ec.pg().barrier();
+    ccsdt_task_counter_close(counter, counter_name, rank == 0);
+    return 0;
+  } catch(const std::exception& e) {
+    g_error = e.what();
+    return 1;
+  }
+}
+
 // host-only: just the op counter through the adapter (usable without a GPU)
 __attribute__((visibility("default"))) int
 adapter_ccsdt_count_ops(int noa, int nob, int nva, int nvb, const int64_t* k_range, const int32_t* k_spin,
