@@ -19,8 +19,9 @@ A "step" is one complete pass of the hot path over the workload.  ONE workload a
             drop-in header (include/ccsd_t_fused_driver_b200.hpp, compiled against the TAMM stand-in in tests/cpp), with
             HOST tensors: every block the tasks touch is pulled through Tensor::get -> fetch callback -> pinned ring ->
             H2D inside the timed region, a fresh context (cold HBM block store) per step, the energies read back.
-            Across ranks the e2e step uses the static cost-balanced split (each rank's host store then only holds the
-            blocks of its own tasks; with the shared counter any rank could draw any task).
+            Across ranks the header's single-node defaults apply: shared-counter hand-out and the node-shared block
+            store (ccsdt_share_attach: a block crosses PCIe once per node, the other ranks copy it from the fetching
+            rank's HBM over NVLink); h2d_bytes_per_step and peer_bytes_per_step are summed over the ranks.
 `benzene` = (N = 1 only) BASELINE.json configs[1], the benzene cc-pVDZ shape (O=21, V=93 per spin, ccsdt_tilesize 40 ->
             28 kernel tasks, 1.59e13 counted flops), the WHOLE job: its own value / e2e (through the same C++ header, dense
             host tensors) / roofline, as a second, named line inside the JSON.
@@ -337,7 +338,8 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-            keys = ["counted_flops", "kernel_launches", "tasks_run", "h2d_bytes", "d2h_bytes", "evaluated_flops", "executed_flops"]
+            keys = ["counted_flops", "kernel_launches", "tasks_run", "h2d_bytes", "d2h_bytes", "evaluated_flops", "executed_flops",
+                    "blocks_from_peers", "peer_bytes"]
             f = torch.tensor([agg[k] for k in keys], dtype=torch.float64, device="cuda")
             dist.all_reduce(f)
             for k, v in zip(keys, f.tolist()):
@@ -379,7 +381,14 @@ def main():
                 assert L.ccsdt_comm_unique_id(uid) == 0
             box = [uid.raw]
             dist.broadcast_object_list(box, src=0)
-            ctx.comm_init(box[0], rank, world)
+            sys.stdout.flush()
+            saved = os.dup(1)                  # NCCL announces its version on stdout: keep the one JSON line alone there
+            os.dup2(2, 1)
+            try:
+                ctx.comm_init(box[0], rank, world)
+            finally:
+                os.dup2(saved, 1)
+                os.close(saved)
 
         def step_resident():
             if counter is not None:
@@ -463,14 +472,26 @@ def main():
             sub = np.ascontiguousarray(task_ids, np.int64) if spec != "all" else None
             opt = H.options(**{k: v for k, v in base_opts.items() if k not in ("rank", "nranks")})
             # ranks of the C++ header's ExecutionContext (TAMM stand-in): rank / size from the environment, meeting in a
-            # POSIX shared-memory segment; static split inside execute for the e2e step (see the module docstring)
+            # POSIX shared-memory segment.  On one node the header's defaults apply: shared-counter hand-out and the
+            # node-shared block store (a block crosses PCIe once per node, the other ranks copy it over NVLink).
+            shim_env = {}
             if world > 1:
-                key = f"bench{os.environ.get('MASTER_PORT', '0')}"
+                key = f"bench{os.environ.get('MASTER_PORT', '0')}{w['key']}"
                 if rank == 0:
                     with open(f"/dev/shm/tamm_shim_{key}", "wb") as f:
                         f.write(b"\0" * 4096)
                 dist.barrier()
-                os.environ.update(TAMM_SHIM_RANK=str(rank), TAMM_SHIM_SIZE=str(world), TAMM_SHIM_KEY=key, CCSDT_B200_DYNAMIC="0")
+                shim_env = dict(TAMM_SHIM_RANK=str(rank), TAMM_SHIM_SIZE=str(world), TAMM_SHIM_KEY=key, CCSDT_B200_COUNTER_KEY=key)
+                # with a dynamic hand-out any rank may be asked for any block: every rank's host table then holds all blocks
+                # of the sample (filled by one single-rank pass before the timed steps).  Without the host memory for
+                # that, the e2e step falls back to the static split, where a rank only ever touches its own blocks.
+                avail = 0
+                for ln in open("/proc/meminfo"):
+                    if ln.startswith("MemAvailable"):
+                        avail = int(ln.split()[1]) * 1024
+                e2e_dynamic = dense_host or avail > world * 40e9
+                if not e2e_dynamic:
+                    shim_env.update(CCSDT_B200_DYNAMIC="0")
             if dense_host:
                 O, V = int(sp.k_range[:sp.noab].sum()), int(sp.k_range[sp.noab:].sum())
                 dims = {drv.T1: (V, O, 1, 1), drv.T2: (V, V, O, O), drv.V_IJAB: (O, O, V, V), drv.V_IJKA: (O, O, O, V),
@@ -508,7 +529,12 @@ def main():
                     return float(out4[0]), float(out4[1]), stats_dict(st, _lib)
                 host_kind = ("host block table: every block the tasks touch is one contiguous host buffer (a local TAMM block), "
                              "filled by the device generator on first touch during the warm-up step; Tensor::get is one memcpy")
+            if world > 1 and not dense_host and e2e_dynamic:
+                step_e2e()                      # single-rank pass over the whole sample: fills this rank's host table
+            os.environ.update(shim_env)
             dt2, agg2, e_e2e = timed(step_e2e, n2, 1)
+            for k in shim_env:
+                os.environ.pop(k, None)
             if not dense_host:
                 info = np.zeros(3, np.int64)
                 H.L.adapter_table_info(table, info.ctypes.data_as(_lib._i64p))
@@ -520,12 +546,15 @@ def main():
                           "host_tensor_bytes_rank0": host_bytes, "blocks_fetched_per_step_rank0": int(agg2["blocks_fetched"] / n2),
                           "seconds_in_Tensor_get_per_step_rank0": agg2["seconds_fetch"] / n2,
                           "seconds_kernel_per_step_rank0": agg2["seconds_kernel"] / n2,
+                          "blocks_from_peers_per_step": int(agg2.get("blocks_from_peers_all", 0) / n2),
+                          "peer_bytes_per_step": int(agg2.get("peer_bytes_all", 0) / n2),
                           "max_rel_energy_diff_vs_device_generated": max(abs(e_e2e[0] - energies[0]) / abs(energies[0]),
                                                                          abs(e_e2e[1] - energies[1]) / abs(energies[1])),
                           "api": "CCSD_T_Fused_Driver<double>::execute of include/ccsd_t_fused_driver_b200.hpp (C++ drop-in header over "
                                  "the C ABI), called as exachem/cc/ccsd_t/ccsd_t.cpp:253-256 does; context created and destroyed inside "
                                  "every call, HBM block store cold at the start of every step; " + host_kind +
-                                 ("" if world == 1 else "; static cost-balanced split across the ranks")}
+                                 ("" if world == 1 else ("; shared-counter hand-out and node-shared block store (the header's defaults on one node)"
+                                                         if e2e_dynamic else "; static cost-balanced split across the ranks, private block stores"))}
         return out
 
     res = measure(w, spec, args.steps, args.warmup, not args.no_e2e, dense_host=(w is BENZENE))
@@ -546,10 +575,14 @@ def main():
     if rank == 0:
         if not args.no_cpu_baseline:
             try:
-                os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-                cb = cpu_reference_sample(w)
-                cb.pop("seconds", None)
-                line["cpu_baseline"] = cb
+                # a clean process: torchrun pins OMP_NUM_THREADS=1 and the OpenMP runtime of this one has read it already
+                env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+                for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+                    env.pop(k, None)
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                                      "--workload", args.workload], env=env, capture_output=True, text=True, timeout=900)
+                ref_line = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+                line["cpu_baseline"] = ref_line["cpu_baseline"]
             except Exception as ex:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "error": repr(ex)}
         print(json.dumps(line), flush=True)

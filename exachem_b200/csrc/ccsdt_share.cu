@@ -10,8 +10,9 @@
 //     the entry's reader count, maps the owner's slab (cudaIpcOpenMemHandle, once per slab) and copies the block into its
 //     own store device-to-device on its fetch stream -- NVLink / NVSwitch, no host involved.  Absent: it inserts the entry
 //     as FETCHING, pulls the block through the fetch callback as usual and publishes it (READY) once its host-to-device
-//     copy has completed.  FETCHING elsewhere: it does not wait, it fetches a private copy.
-//   * The owner never evicts a block with readers; a reader drops its count when its copy has completed (events polled).
+//     copy has completed (a host function queued behind the copy on the fetch stream).  FETCHING elsewhere: it waits a
+//     few milliseconds for the owner's upload, then copies from it; past 50 ms it fetches a private copy instead.
+//   * The owner never evicts a block with readers; a reader drops its count when its copy has completed.
 //   * Detach: a barrier among the attached ranks (nobody is still reading), then mappings are closed and slabs freed.
 #include "ccsdt_ctx.hpp"
 
@@ -68,13 +69,23 @@ struct ShareState {
   std::vector<Slab> slabs;
   std::map<size_t, std::vector<std::pair<int, size_t>>> free_list; // exact-size reuse: block sizes repeat heavily
   std::map<std::pair<int, int>, void*>                  peer_base; // (rank, slab) -> mapped base
-  struct Pending {
-    ShareEntry* e;
-    cudaEvent_t ev;
-    bool        publish; // true: my H2D copy -> READY; false: my peer copy -> readers--
-  };
-  std::vector<Pending> pending;
 };
+
+// runs on a CUDA callback thread when the copy queued before it on the fetch stream has completed: an upload publishes
+// its block (FETCHING -> READY, unless the owner dropped it meanwhile), a peer copy gives the owner's block back
+struct CopyDone {
+  ShareEntry* e;
+  bool        publish;
+};
+static void CUDART_CB copy_done(void* p) {
+  auto* d = static_cast<CopyDone*>(p);
+  if(d->publish) {
+    uint32_t expect = kFetching;
+    __atomic_compare_exchange_n(&d->e->state, &expect, kReady, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+  }
+  else __atomic_fetch_sub(&d->e->readers, 1u, __ATOMIC_ACQ_REL);
+  delete d;
+}
 
 static uint64_t pack_key(const BlockKey& k) {
   return (((uint64_t) k.tensor << 60) | ((uint64_t) k.b[0] << 45) | ((uint64_t) k.b[1] << 30) | ((uint64_t) k.b[2] << 15) |
@@ -182,23 +193,10 @@ void share_free(ccsdt_ctx* ctx, int slab, size_t offset, size_t bytes) {
   ctx->share->free_list[bytes].push_back({slab, offset});
 }
 
-// completes what can be completed without blocking: publishes blocks whose upload has landed, releases the reader count
-// of peer copies that have finished
+// every copy this rank has queued on its fetch stream has completed: its uploads are published, the blocks it copied from
+// peers are given back
 void share_poll(ccsdt_ctx* ctx, bool wait) {
-  ShareState* s = ctx->share;
-  if(!s) return;
-  size_t w = 0;
-  for(size_t i = 0; i < s->pending.size(); i++) {
-    ShareState::Pending& p = s->pending[i];
-    if(wait) cudaEventSynchronize(p.ev);
-    if(wait || cudaEventQuery(p.ev) == cudaSuccess) {
-      if(p.publish) __atomic_store_n(&p.e->state, kReady, __ATOMIC_RELEASE);
-      else __atomic_fetch_sub(&p.e->readers, 1u, __ATOMIC_ACQ_REL);
-      cudaEventDestroy(p.ev);
-    }
-    else s->pending[w++] = p;
-  }
-  s->pending.resize(w);
+  if(ctx->share && wait && ctx->s_fetch) cudaStreamSynchronize(ctx->s_fetch);
 }
 
 // A block that is not in this rank's store.  Returns 1 when a peer copy was issued into *dev (the block is on its way),
@@ -206,61 +204,63 @@ void share_poll(ccsdt_ctx* ctx, bool wait) {
 // upload (NULL: private copy) -- and < 0 on out-of-memory (evict and retry) or > 1 on error.
 int share_acquire(ccsdt_ctx* ctx, const BlockKey& key, size_t bytes, double** dev, int* slab, size_t* offset, void** entry) {
   ShareState* s = ctx->share;
-  share_poll(ctx, false);
   *entry = nullptr;
   if(int rc = share_alloc(ctx, bytes, dev, slab, offset)) return rc < 0 ? -1 : 2;
   const uint64_t k = pack_key(key);
-  share_lock(s);
-  ShareEntry* e = share_find(s, k, true);
-  if(e && e->state == kReady && e->owner != s->rank && e->bytes == bytes) {
-    e->readers++;
-    const int    owner = e->owner, oslab = e->slab;
-    const size_t ooff = e->offset;
-    share_unlock(s);
-    auto pb = s->peer_base.find({owner, oslab});
-    if(pb == s->peer_base.end()) {
-      void*       base = nullptr;
-      cudaError_t ce   = cudaIpcOpenMemHandle(&base, s->hdr->ranks[owner].handle[oslab], cudaIpcMemLazyEnablePeerAccess);
-      if(ce != cudaSuccess) {
-        cudaGetLastError();
-        __atomic_fetch_sub(&e->readers, 1u, __ATOMIC_ACQ_REL);
-        return 0; // no peer path between the two devices: fetch from the host, privately
+  const auto     t0 = std::chrono::steady_clock::now();
+  for(;;) {
+    share_lock(s);
+    ShareEntry* e = share_find(s, k, true);
+    if(e && e->state == kFetching && e->owner != s->rank &&
+       std::chrono::steady_clock::now() - t0 < std::chrono::milliseconds(50)) {
+      share_unlock(s); // another rank is uploading it right now: cheaper to wait for that than to fetch it again
+      std::this_thread::sleep_for(std::chrono::microseconds(20));
+      continue;
+    }
+    if(e && e->state == kReady && e->owner != s->rank && e->bytes == bytes) {
+      e->readers++;
+      const int    owner = e->owner, oslab = e->slab;
+      const size_t ooff = e->offset;
+      share_unlock(s);
+      auto pb = s->peer_base.find({owner, oslab});
+      if(pb == s->peer_base.end()) {
+        void*       base = nullptr;
+        cudaError_t ce   = cudaIpcOpenMemHandle(&base, s->hdr->ranks[owner].handle[oslab], cudaIpcMemLazyEnablePeerAccess);
+        if(ce != cudaSuccess) {
+          cudaGetLastError();
+          __atomic_fetch_sub(&e->readers, 1u, __ATOMIC_ACQ_REL);
+          return 0; // no peer path between the two devices: fetch from the host, privately
+        }
+        pb = s->peer_base.emplace(std::make_pair(owner, oslab), base).first;
       }
-      pb = s->peer_base.emplace(std::make_pair(owner, oslab), base).first;
+      cudaError_t ce = cudaMemcpyAsync(*dev, (const char*) pb->second + ooff, bytes, cudaMemcpyDefault, ctx->s_fetch);
+      if(ce == cudaSuccess) ce = cudaLaunchHostFunc(ctx->s_fetch, copy_done, new CopyDone{e, false});
+      if(ce != cudaSuccess) {
+        __atomic_fetch_sub(&e->readers, 1u, __ATOMIC_ACQ_REL);
+        return ctx->fail(std::string("peer copy failed: ") + cudaGetErrorString(ce), 2);
+      }
+      ctx->fetch_dirty = true;
+      ctx->stats.blocks_from_peers++;
+      ctx->stats.peer_bytes += (int64_t) bytes;
+      return 1;
     }
-    cudaError_t ce = cudaMemcpyAsync(*dev, (const char*) pb->second + ooff, bytes, cudaMemcpyDefault, ctx->s_fetch);
-    cudaEvent_t ev = nullptr;
-    if(ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    if(ce == cudaSuccess) ce = cudaEventRecord(ev, ctx->s_fetch);
-    if(ce != cudaSuccess) {
-      __atomic_fetch_sub(&e->readers, 1u, __ATOMIC_ACQ_REL);
-      return ctx->fail(std::string("peer copy failed: ") + cudaGetErrorString(ce), 2);
+    if(e && e->state == kEmpty) { // absent: this rank fetches it for the node
+      e->state  = kFetching;
+      e->owner  = s->rank;
+      e->slab   = *slab;
+      e->offset = *offset;
+      e->bytes  = bytes;
+      *entry    = e;
     }
-    s->pending.push_back({e, ev, false});
-    ctx->fetch_dirty = true;
-    ctx->stats.blocks_from_peers++;
-    ctx->stats.peer_bytes += (int64_t) bytes;
-    return 1;
+    share_unlock(s);
+    return 0;
   }
-  if(e && e->state == kEmpty) { // absent: this rank fetches it for the node
-    e->state  = kFetching;
-    e->owner  = s->rank;
-    e->slab   = *slab;
-    e->offset = *offset;
-    e->bytes  = bytes;
-    *entry    = e;
-  }
-  share_unlock(s);
-  return 0;
 }
 
 // the upload of a block this rank fetches for the node has been issued: publish it when `ev`'s copy has landed
 int share_publish_after(ccsdt_ctx* ctx, void* entry, cudaStream_t st) {
   if(!entry) return 0;
-  cudaEvent_t ev = nullptr;
-  CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CK(cudaEventRecord(ev, st));
-  ctx->share->pending.push_back({(ShareEntry*) entry, ev, true});
+  CK(cudaLaunchHostFunc(st, copy_done, new CopyDone{(ShareEntry*) entry, true}));
   return 0;
 }
 
@@ -276,10 +276,7 @@ bool share_release(ccsdt_ctx* ctx, const BlockKey& key, BlockEntry& be, bool wai
       std::this_thread::sleep_for(std::chrono::microseconds(50));
       share_lock(s);
     }
-    // an upload that has not been published yet must not publish a freed block
-    for(auto& p: s->pending)
-      if(p.e == e && p.publish) p.publish = false, __atomic_fetch_add(&e->readers, 1u, __ATOMIC_ACQ_REL);
-    e->state = kTomb;
+    e->state = kTomb; // (an upload still in flight finds the entry no longer FETCHING and does not publish it)
   }
   share_unlock(s);
   share_free(ctx, be.slab, be.offset, be.bytes);

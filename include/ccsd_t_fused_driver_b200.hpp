@@ -213,16 +213,17 @@ std::tuple<T, T, double, double> CCSD_T_Fused_Driver<T>::execute(
       CCSDT_B200_TERMINATE("[CCSD(T) B200] cannot attach to the shared task counter " + counter_name);
     }
     check(ccsdt_set_task_counter(ctx, counter));
-    // ... and the node-shared block store: a block is fetched through Tensor::get by ONE rank of the node and read from
-    // its HBM by the others (CCSDT_B200_SHARE=0 keeps every rank's store private)
-    bool share = true;
-    if(const char* e = std::getenv("CCSDT_B200_SHARE")) share = std::atoi(e) != 0;
-    if(share) {
-      const std::string dir = "/ccsdt_b200_dir_" + std::to_string((long) getuid()) + "_" + (key ? key : "0");
-      if(rank == 0) check(ccsdt_share_attach(ctx, dir.c_str(), rank, nranks, 1));
-      ec.pg().barrier();
-      if(rank != 0) check(ccsdt_share_attach(ctx, dir.c_str(), rank, nranks, 0));
-    }
+  }
+  // The node-shared block store (also with the static split): a block is fetched through Tensor::get by ONE rank of the
+  // node and read from its HBM by the others (CCSDT_B200_SHARE=0 keeps every rank's store private)
+  bool share = nranks > 1 && CCSDT_B200_SINGLE_NODE(ec);
+  if(const char* e = std::getenv("CCSDT_B200_SHARE")) share = share && std::atoi(e) != 0;
+  if(share) {
+    const char*       key = std::getenv("CCSDT_B200_COUNTER_KEY");
+    const std::string dir = "/ccsdt_b200_dir_" + std::to_string((long) getuid()) + "_" + (key ? key : "0");
+    if(rank == 0) check(ccsdt_share_attach(ctx, dir.c_str(), rank, nranks, 1));
+    ec.pg().barrier();
+    if(rank != 0) check(ccsdt_share_attach(ctx, dir.c_str(), rank, nranks, 0));
   }
 
   double energies[2] = {0.0, 0.0};
