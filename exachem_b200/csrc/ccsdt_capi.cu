@@ -812,6 +812,10 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
     // clock, so the LRU does not take them back before they are used.
     const int64_t lookahead = (!ctx->task_counter && fetching && ctx->opt.prefetch_tasks >= 0)
                                 ? (ctx->opt.prefetch_tasks > 0 ? ctx->opt.prefetch_tasks : ((int64_t) 1 << 40)) : 0;
+    // Dynamic hand-out: the next task is not known before it is claimed, so a rank claims ONE task ahead and fetches
+    // that task's blocks while it waits for the GPU (the tail of the list is the cheap tasks: holding one of them does
+    // not unbalance the ranks).
+    const bool claim_ahead = ctx->task_counter && fetching && ctx->opt.prefetch_tasks >= 0;
     int64_t               pf_task = 0;      // next entry of `order` whose blocks have not been listed
     std::vector<SrcPiece> pf_queue, scratch;
     size_t                pf_pos   = 0;
@@ -844,9 +848,18 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
       return 0;
     };
 
+    int64_t               claimed = claim_ahead ? next_task() : -2; // -2: not used
+    std::vector<SrcPiece> ahead;                                      // missing blocks of the task claimed ahead
+    size_t                ahead_pos = 0;
     for(int64_t j = 0;; j++) {
-      const int64_t ti = next_task();
+      const int64_t ti = claim_ahead ? claimed : next_task();
       if(ti < 0) break;
+      if(claim_ahead) {
+        claimed = next_task();
+        ahead.clear();
+        ahead_pos = 0;
+        if(claimed >= 0 && j > 0) missing_blocks(ctx, ctx->tasks[claimed], ahead, scratch);
+      }
       mine.push_back(ti);
       StageBuf& b = ctx->buf[j % nbuf];
       // the buffer's previous task must have finished computing before its panels are rebuilt
@@ -867,6 +880,19 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
       if(ctx->opt.verbose >= 2) {
         b.trace_slot = (int64_t) ctx->trace.size();
         ctx->trace.push_back(TraceRow{ti, tr0, now_s() - t0, ctx->stats.seconds_fetch - tf0, 0, 0, 0, 0});
+      }
+      if(claim_ahead && claimed >= 0) {
+        // task j is queued: pull the blocks of the task claimed ahead while the GPU works on j - 1 and j (the first
+        // time round its list is made only now, so that the very first task starts as early as possible)
+        if(j == 0) missing_blocks(ctx, ctx->tasks[claimed], ahead, scratch);
+        StageBuf& nb = ctx->buf[(j + 1) % nbuf];
+        while(ahead_pos < ahead.size() && nb.timing_pending && cudaEventQuery(nb.done) == cudaErrorNotReady) {
+          const SrcPiece& p = ahead[ahead_pos++];
+          if(ctx->blocks.count(p.key)) continue;
+          if(ctx->block_budget && ctx->block_bytes + p.elems * 8 > ctx->block_budget) break;
+          BlockRef ref;
+          if(int rc = resolve_block(ctx, p.key, p.elems, ctx->use_clock + 1, ref)) return rc;
+        }
       }
       const double ops = (double) task_ops(ctx->sp, ctx->tasks[ti]);
       ctx->stats.counted_flops += ops;

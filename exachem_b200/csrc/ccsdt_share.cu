@@ -4,8 +4,8 @@
 // cache, exachem/cc/ccsd_t/ccsd_t.cpp:236-241).
 //
 //   * A POSIX shared-memory segment holds a hash table  block id -> (owner rank, slab, offset, state, readers)  and, per
-//     rank, the CUDA IPC handles of the slabs its block store is carved from (cudaMalloc'ed 1 GiB at a time: pool
-//     allocations of cudaMallocAsync cannot be exported as legacy IPC handles).
+//     rank, the CUDA IPC handles of the slabs its block store is carved from (cudaMalloc'ed 256 MiB to 4 GiB at a time:
+//     pool allocations of cudaMallocAsync cannot be exported as legacy IPC handles).
 //   * A rank that needs a block looks it up under the segment's process-shared mutex.  READY at another rank: it bumps
 //     the entry's reader count, maps the owner's slab (cudaIpcOpenMemHandle, once per slab) and copies the block into its
 //     own store device-to-device on its fetch stream -- NVLink / NVSwitch, no host involved.  Absent: it inserts the entry
@@ -32,7 +32,7 @@ namespace ccsdt {
 
 constexpr int      kMaxRanks = 16, kMaxSlabs = 256;
 constexpr uint32_t kEmpty = 0, kFetching = 1, kReady = 2, kTomb = 3;
-constexpr size_t   kSlabBytes = (size_t) 1 << 30;
+constexpr size_t   kSlabBytes = (size_t) 4 << 30;
 
 struct ShareEntry {
   uint64_t key;     // tensor << 60 | bid[0] << 45 | bid[1] << 30 | bid[2] << 15 | bid[3], + 1 (0 = never used)
@@ -164,7 +164,9 @@ int share_alloc(ccsdt_ctx* ctx, size_t bytes, double** dev, int* slab, size_t* o
     }
     if((int) s->slabs.size() >= kMaxSlabs) return ctx->fail("shared block store: slab table full", 2);
     Slab sl;
-    sl.bytes = std::max(kSlabBytes, bytes);
+    // 256 MiB to start with, doubling up to 4 GiB: few slabs (each costs its peers one cudaIpcOpenMemHandle) without
+    // reserving gigabytes for a job of megabytes
+    sl.bytes = std::max(std::min<size_t>((size_t) 256 << 20 << std::min<size_t>(s->slabs.size(), 4), kSlabBytes), bytes);
     cudaError_t e = cudaMalloc((void**) &sl.base, sl.bytes);
     if(e != cudaSuccess) {
       cudaGetLastError();
