@@ -20,7 +20,7 @@ class Options(C.Structure):
                 ("ctas_per_sm", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
                 ("overlap", C.c_int32), ("stagger", C.c_int32), ("verbose", C.c_int32), ("symmetry", C.c_int32),
                 ("exec_tilesize", C.c_int32), ("prefetch_tasks", C.c_int32), ("block_budget_bytes", C.c_int64),
-                ("watchdog_ms", C.c_int32), ("reserved_", C.c_int32)]
+                ("watchdog_ms", C.c_int32), ("check_symmetry", C.c_int32)]
 
 
 class Stats(C.Structure):

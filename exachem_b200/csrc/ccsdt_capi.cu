@@ -803,6 +803,7 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
     CK(cudaEventRecord(ctx->ev_base, ctx->s_compute));
     CK(cudaStreamWaitEvent(ctx->s_compute2, ctx->ev_base, 0));
     ctx->kernel_busy_until = 0.0;
+    if(int rc = check_dense_symmetry(ctx)) return rc;
 
     // Prefetch (static hand-out, blocks through the callback): while the host would only wait for the GPU to
     // release a staging buffer, it pulls the blocks of the tasks to come into HBM -- the callback (the caller's
@@ -911,6 +912,13 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
     uint32_t flag = 0;
     CK(cudaMemcpy(&flag, ctx->d_error, 4, cudaMemcpyDeviceToHost));
     if(flag) return ctx->fail("device error flag " + std::to_string(flag), 9);
+    if(ctx->opt.symmetry && ctx->opt.check_symmetry >= 0) {
+      CK(cudaStreamSynchronize(ctx->s_fetch));
+      CK(cudaMemcpy(&flag, ctx->d_symflag, 4, cudaMemcpyDeviceToHost));
+      if(flag)
+        return ctx->fail("an operand is not antisymmetric (T2 in (a,b) / (i,j), v2ijab in (i,j) / (a,b), v2ijka in (i,j), v2iabc in (b,c)): "
+                         "options.symmetry = 1 relies on it -- set symmetry = 0 to evaluate every element as the reference does", 12);
+    }
     std::vector<double> e_host((size_t) 2 * std::max<int64_t>(n, 1));
     if(n) CK(cudaMemcpy(e_host.data(), ctx->d_task_energy, (size_t) n * 16, cudaMemcpyDeviceToHost));
     ctx->stats.d2h_bytes += n * 16;
@@ -984,6 +992,7 @@ static void real_destroy(ccsdt_ctx* ctx) {
   if(ctx->d_evl) cudaFree(ctx->d_evl);
   if(ctx->d_task_energy) cudaFree(ctx->d_task_energy);
   if(ctx->d_error) cudaFree(ctx->d_error);
+  if(ctx->d_symflag) cudaFree(ctx->d_symflag);
   for(auto& kv: ctx->box_lists)
     if(kv.second.dev) cudaFree(kv.second.dev);
   if(ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
@@ -1082,6 +1091,8 @@ int ccsdt_create(ccsdt_ctx** out, int device) {
   }
   if((e = cudaMalloc(&ctx->d_error, 16)) != cudaSuccess) return bail(cudaGetErrorString(e));
   cudaMemset(ctx->d_error, 0, 16);
+  if((e = cudaMalloc(&ctx->d_symflag, 4)) != cudaSuccess) return bail(cudaGetErrorString(e));
+  cudaMemset(ctx->d_symflag, 0, 4);
   if((e = fused_dmma_configure((size_t) ctx->prop.sharedMemPerBlockOptin - 2048)) != cudaSuccess)
     return bail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
   if(store_create(ctx)) return bail(ctx->err);
@@ -1252,6 +1263,7 @@ int ccsdt_set_space(ccsdt_ctx* ctx, int noa, int nob, int nva, int nvb, const in
   cudaSetDevice(ctx->device);
   sync_streams(ctx);
   free_operands(ctx);
+  CK(cudaMemset(ctx->d_symflag, 0, 4)); // the operands of the previous space are gone, and their verdict with them
   ctx->store      = sp;
   ctx->have_space = true;
   if(int rc = rebuild_exec(ctx)) return rc;

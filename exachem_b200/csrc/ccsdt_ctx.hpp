@@ -137,7 +137,9 @@ struct ccsdt_ctx {
   bool            pools_ready = false;
   double*         d_task_energy = nullptr;
   int64_t         task_energy_cap = 0;
-  uint32_t*       d_error = nullptr;
+  uint32_t*       d_error = nullptr;   // [0] error word of the fused kernel, [1..2] watchdog limit, [3] unused
+  uint32_t*       d_symflag = nullptr; // set by antisym_check_kernel: an operand is not antisymmetric (options.symmetry)
+  bool            dense_check_pending[5] = {false, false, false, false, false};
   cudaStream_t    s_compute = nullptr, s_compute2 = nullptr, s_stage = nullptr;
   cudaEvent_t     ev_base = nullptr;   // start of the current run: kernel intervals are placed on its time line
   double          kernel_busy_until = 0.0; // end (ms after ev_base) of the union of fused-kernel intervals so far
@@ -207,6 +209,9 @@ int  resolve_block(ccsdt_ctx* ctx, const BlockKey& key, size_t elems, int64_t fo
 int  resolve_dense(ccsdt_ctx* ctx, int tensor, const uint32_t exec_bid[4], BlockRef& out);
 // records ev_fetched after the copies issued so far and makes `st` wait for it
 int  fetch_fence(ccsdt_ctx* ctx, cudaStream_t st);
+// queues the antisymmetry checks (options.symmetry / check_symmetry) of a storage block on `st`, of the dense tensors on s_stage
+int  check_block_symmetry(ccsdt_ctx* ctx, const BlockKey& key, const double* dev, cudaStream_t st);
+int  check_dense_symmetry(ccsdt_ctx* ctx);
 
 // ---- ccsdt_share.cu ----
 int    share_acquire(ccsdt_ctx* ctx, const BlockKey& key, size_t bytes, double** dev, int* slab, size_t* offset, void** entry);

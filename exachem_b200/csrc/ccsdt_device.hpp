@@ -146,6 +146,7 @@ cudaError_t launch_fused_simple(const TaskParams& p, cudaStream_t st, int* grid_
 cudaError_t launch_reduce_partials(const double* partial, int n, double* out2, cudaStream_t st);
 cudaError_t launch_zero(double* a, int64_t na, uint32_t* b, int nb, cudaStream_t st);
 cudaError_t launch_copy_from_pinned(const void* pinned_host, void* dev, size_t bytes, cudaStream_t st);
+cudaError_t launch_antisym_check(const double* A, const int64_t n[4], const int64_t st[4], int pair, uint32_t* flag, cudaStream_t stream);
 cudaError_t fused_dmma_configure(size_t smem_bytes);
 int         fused_dmma_max_ctas_per_sm(int threads, size_t smem_bytes);
 

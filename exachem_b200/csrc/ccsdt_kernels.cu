@@ -98,6 +98,37 @@ cudaError_t launch_zero(double* a, int64_t na, uint32_t* b, int nb, cudaStream_t
   return cudaGetLastError();
 }
 
+// Antisymmetry of a 4-index array in dimensions (PAIR, PAIR + 1), which must have the same extent: sets *flag when
+// A[..x,y..] + A[..y,x..] is not zero to rounding.  Guards options.symmetry (the box skipping of the fused kernel
+// assumes t3 antisymmetric in same-spin indices, i.e. antisymmetric T2 / V2); element strides are passed, so the same
+// kernel checks a block of the block store and a whole dense tensor.
+__global__ void __launch_bounds__(256) antisym_check_kernel(const double* __restrict__ A, int64_t n0, int64_t n1, int64_t n2, int64_t n3,
+                                                            int64_t s0, int64_t s1, int64_t s2, int64_t s3, int pair,
+                                                            uint32_t* __restrict__ flag) {
+  const int64_t total = n0 * n1 * n2 * n3;
+  for(int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t) gridDim.x * blockDim.x) {
+    int64_t r = e, i[4];
+    i[3] = r % n3; r /= n3;
+    i[2] = r % n2; r /= n2;
+    i[1] = r % n1;
+    i[0] = r / n1;
+    if(i[pair] > i[pair + 1]) continue;
+    const double  x = A[i[0] * s0 + i[1] * s1 + i[2] * s2 + i[3] * s3];
+    const int64_t t = i[pair];
+    i[pair] = i[pair + 1], i[pair + 1] = t;
+    const double y = A[i[0] * s0 + i[1] * s1 + i[2] * s2 + i[3] * s3];
+    if(fabs(x + y) > 1e-9 * (fabs(x) + fabs(y)) + 1e-14) atomicOr(flag, 1u);
+  }
+}
+
+cudaError_t launch_antisym_check(const double* A, const int64_t n[4], const int64_t st[4], int pair, uint32_t* flag, cudaStream_t stream) {
+  const int64_t total = n[0] * n[1] * n[2] * n[3];
+  if(total <= 0 || n[pair] != n[pair + 1]) return cudaSuccess;
+  const unsigned grid = (unsigned) std::min<int64_t>((total + 255) / 256, 148 * 8);
+  antisym_check_kernel<<<grid, 256, 0, stream>>>(A, n[0], n[1], n[2], n[3], st[0], st[1], st[2], st[3], pair, flag);
+  return cudaGetLastError();
+}
+
 // =================================================================================================
 // shared epilogue pieces
 // =================================================================================================

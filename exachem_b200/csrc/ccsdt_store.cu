@@ -293,6 +293,7 @@ int resolve_block(ccsdt_ctx* ctx, const BlockKey& key, size_t elems, int64_t for
     it = ctx->blocks.emplace(key, be).first;
     if(int rc = share_publish_after(ctx, dir_entry, ctx->s_fetch)) return rc;
     }
+    if(int rc = check_block_symmetry(ctx, key, dev, ctx->s_fetch)) return rc;
   }
   it->second.last_use = std::max(it->second.last_use, for_clock);
   // row-major strides of the storage block
@@ -328,6 +329,49 @@ int fetch_fence(ccsdt_ctx* ctx, cudaStream_t st) {
   CK(cudaEventRecord(ctx->ev_fetched, ctx->s_fetch));
   CK(cudaStreamWaitEvent(st, ctx->ev_fetched, 0));
   ctx->fetch_dirty = false;
+  return 0;
+}
+
+// which index pairs of a tensor are antisymmetric: first dimension of each pair, -1 = none
+static const int kAntiPairs[5][2] = {{-1, -1}, {0, 2}, {0, 2}, {0, -1}, {2, -1}};
+
+int check_block_symmetry(ccsdt_ctx* ctx, const BlockKey& key, const double* dev, cudaStream_t st) {
+  if(!ctx->opt.symmetry || ctx->opt.check_symmetry < 0) return 0;
+  const char* kinds = kKinds[key.tensor];
+  for(int q = 0; q < 2; q++) {
+    const int pair = kAntiPairs[key.tensor][q];
+    if(pair < 0 || key.b[pair] != key.b[pair + 1]) continue; // visible inside one block only when the two tiles coincide
+    int64_t n[4] = {1, 1, 1, 1}, stv[4] = {0, 0, 0, 0}, acc = 1;
+    for(int d = 3; d >= 0; d--) {
+      n[d]   = ctx->store.k_range[tile_of(ctx->store, kinds[d], key.b[d])];
+      stv[d] = acc;
+      acc *= n[d];
+    }
+    CK(launch_antisym_check(dev, n, stv, pair, ctx->d_symflag, st));
+    ctx->stats.kernel_launches++;
+  }
+  return 0;
+}
+
+int check_dense_symmetry(ccsdt_ctx* ctx) {
+  for(int t = 1; t < 5; t++) {
+    if(!ctx->dense_check_pending[t]) continue;
+    ctx->dense_check_pending[t] = false;
+    if(!ctx->opt.symmetry || ctx->opt.check_symmetry < 0 || !ctx->dense[t]) continue;
+    const char* kinds = kKinds[t];
+    int64_t     n[4], stv[4], acc = 1;
+    for(int d = 3; d >= 0; d--) {
+      n[d]   = dim_full(ctx->sp, kinds[d]);
+      stv[d] = acc;
+      acc *= n[d];
+    }
+    if(ctx->upload_pending[t]) CK(cudaStreamWaitEvent(ctx->s_stage, ctx->ev_full[t], 0));
+    for(int q = 0; q < 2; q++)
+      if(kAntiPairs[t][q] >= 0) {
+        CK(launch_antisym_check(ctx->dense[t], n, stv, kAntiPairs[t][q], ctx->d_symflag, ctx->s_stage));
+        ctx->stats.kernel_launches++;
+      }
+  }
   return 0;
 }
 
@@ -459,6 +503,7 @@ static int put_dense_impl(ccsdt_ctx* ctx, int tensor, const double* host, bool a
   }
   ctx->pending_h2d += sent;                  // reported by the next run's stats
   ctx->synthetic = false;
+  ctx->dense_check_pending[tensor] = true;   // antisymmetry is verified by the next run (options.symmetry)
   return 0;
 }
 
@@ -492,7 +537,7 @@ int ccsdt_put_block(ccsdt_ctx* ctx, int tensor, const uint32_t bid[4], const dou
   CK(cudaMemcpy(dev, host, n * 8, cudaMemcpyHostToDevice));
   ctx->pending_h2d += (int64_t) n * 8;
   ctx->synthetic = false;
-  return 0;
+  return check_block_symmetry(ctx, key, dev, ctx->s_stage);
 }
 
 int ccsdt_set_fetch(ccsdt_ctx* ctx, ccsdt_fetch_fn fn, void* user) {

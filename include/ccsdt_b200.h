@@ -99,7 +99,10 @@ typedef struct ccsdt_options {
                             0 = what is free after the panel pools are allocated, minus a reserve */
   int32_t watchdog_ms;   /* a pipeline wait inside the fused kernel that lasts longer than this traps (reported as a CUDA
                             error) instead of hanging the GPU; 0 = default (20 000 ms of %globaltimer), -1 = never */
-  int32_t reserved_;
+  int32_t check_symmetry; /* with symmetry = 1: 0 (default) = verify on the device, once per block / dense tensor as it arrives,
+                            that T2, v2ijab (both index pairs), v2ijka (i,j) and v2iabc (b,c) are antisymmetric where that can be
+                            seen inside one block (blocks whose two tiles coincide; whole tensors for ccsdt_put_dense) -- the run
+                            fails with a message instead of returning an energy built on a wrong assumption; -1 = skip the check */
 } ccsdt_options;
 
 typedef struct ccsdt_stats {

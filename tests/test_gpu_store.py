@@ -224,3 +224,26 @@ def test_single_rank_nccl_allreduce_through_the_c_abi():
         assert ctx.comm_allreduce(1.5, -2.25) == (1.5, -2.25)
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("how", ["dense", "fetch"])
+def test_symmetry_reduction_refuses_operands_that_are_not_antisymmetric(how, orc):
+    """options.symmetry skips mirror-image boxes, which is only right for antisymmetric T2 / V2: the device check
+    (options.check_symmetry, default on) must turn a violation into an error, and symmetry = 0 must still give the
+    reference's answer on the very same tensors"""
+    g = GOLD["o4v6_ts4"]
+    sp = drv.setup_mo_space(g["noa"], g["nob"], g["nva"], g["nvb"], g["tilesize"])
+    T = dict(syn.dense_all(syn.Orbitals(g["noa"], g["nob"], g["nva"], g["nvb"]), g["seed"]))
+    ok = run(sp, T, True, how=how)                              # antisymmetric as generated: passes
+    assert _close(ok[0], float(g["energy1"]))
+    bad = dict(T)
+    bad["t2"] = T["t2"].copy()
+    bad["t2"][1, 0, 1, 0] += 0.25                               # T2[a,b,i,j] != -T2[b,a,i,j] inside a diagonal block
+    with pytest.raises(drv.CcsdtError, match="not antisymmetric"):
+        run(sp, bad, True, how=how)
+    e1, e2, _ = run(sp, bad, True, how=how, symmetry=0)         # every element evaluated, as the reference does
+    r1, r2 = orc.run(orc.tiles(g["noa"], g["nob"], g["nva"], g["nvb"], g["tilesize"]), bad, True)
+    assert _close(e1, r1) and _close(e2, r2)
+    e1, e2, _ = run(sp, bad, True, how=how, check_symmetry=-1)  # the check can be switched off (the answer is then the caller's risk)
+    assert np.isfinite(e1) and np.isfinite(e2)
+
