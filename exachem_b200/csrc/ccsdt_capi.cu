@@ -499,13 +499,22 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t, std::vector<GatherDes
       if(t.t[4] == t.t[5]) P.sym |= 8;
       if((P.sym & 3) == 3 && P.c[0] == 2) P.sym |= 16;
     }
-    if(P.sym) {
+    // Boundary layers: a hole tile of ODD extent ends in boxes that hold one valid hole index where the sub-box has two
+    // slots; the kernel runs those boxes through half-size instantiations of its k-loops (consume_term<.., SKIP>).  The
+    // boxes are therefore handed out by class -- interior first, then the boundary layer of h1, h2, h3 -- so that the CTAs
+    // of an SM run the same few instantiations at any time (instruction cache); inside a class the brick-major order stays.
+    int odd = 0;
+    for(int j = 0; j < 3; j++)
+      if(P.c[j] == 2 && (ext[j] & 1)) odd |= 1 << j;
+    auto warps_with_work = [](int extent, int off) { return std::max(0, std::min(4, (extent - off + 1) / 2)); };
+    double units_x = 0, units_y = 0;
+    if(P.sym || odd) {
       std::array<int, 19> key;
       for(int i = 0; i < 6; i++) key[i] = P.nbox[i], key[6 + i] = P.brick[i], key[12 + i] = P.nbrick[i];
-      key[18]  = P.sym;
+      key[18]  = P.sym | (odd << 8) | ((ext[3] & 7) << 12) | ((ext[4] & 7) << 16);
       auto& bl = ctx->box_lists[key];
       if(!bl.dev) {
-        std::vector<int32_t> ids;
+        std::vector<int32_t> ids[4]; // class: 0 = interior, 1 + j = boundary layer of hole j
         const int            order[6] = {2, 1, 0, 5, 4, 3}; // same decoding as decode_box (ccsdt_kernel_common.cuh)
         for(int64_t id = 0; id < padded; id++) {
           int     in[6], bx[6];
@@ -522,18 +531,36 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t, std::vector<GatherDes
             r /= P.nbrick[d];
             valid &= bx[d] < P.nbox[d];
           }
-          if(valid && box_weight(P.sym, bx) > 0) ids.push_back((int32_t) id);
+          if(!valid || (P.sym && box_weight(P.sym, bx) <= 0)) continue;
+          int cls = 0;
+          for(int j = 2; j >= 0; j--)
+            if(((odd >> j) & 1) && bx[j] == P.nbox[j] - 1) cls = 1 + j;
+          ids[cls].push_back((int32_t) id);
+          const double per_warp = cls ? 8.0 : 16.0;
+          bl.units_x += per_warp * warps_with_work(ext[3], bx[3] * PBOX);
+          bl.units_y += per_warp * warps_with_work(ext[4], bx[4] * PBOX);
         }
-        bl.n = (int32_t) ids.size();
-        CK(cudaMalloc(&bl.dev, sizeof(int32_t) * std::max<size_t>(ids.size(), 1)));
-        CK(cudaMemcpy(bl.dev, ids.data(), sizeof(int32_t) * ids.size(), cudaMemcpyHostToDevice));
+        std::vector<int32_t> all;
+        for(auto& v: ids) all.insert(all.end(), v.begin(), v.end());
+        bl.n = (int32_t) all.size();
+        CK(cudaMalloc(&bl.dev, sizeof(int32_t) * std::max<size_t>(all.size(), 1)));
+        CK(cudaMemcpy(bl.dev, all.data(), sizeof(int32_t) * all.size(), cudaMemcpyHostToDevice));
       }
       P.box_list = bl.dev;
       P.nlist    = bl.n;
       nboxes     = bl.n;
       b.grid     = (int) std::max<int64_t>(1, std::min<int64_t>(nboxes, in_flight));
+      units_x = bl.units_x, units_y = bl.units_y;
     }
-    b.eval_fraction = (double) nboxes / (double) P.nboxes;
+    else {
+      // no list: every box runs the full loops; warps whose tile-particle slots are all outside the tile idle
+      double wx = 0, wy = 0;
+      for(int bq = 0; bq < P.nbox[3]; bq++) wx += warps_with_work(ext[3], bq * PBOX);
+      for(int bq = 0; bq < P.nbox[4]; bq++) wy += warps_with_work(ext[4], bq * PBOX);
+      units_x = 16.0 * (double) P.nboxes / P.nbox[3] * wx;
+      units_y = 16.0 * (double) P.nboxes / P.nbox[4] * wy;
+    }
+    b.eval_fraction = (P.sym ? (double) nboxes : (double) P.nboxes) / (double) P.nboxes;
     // one box keeps the tensor pipe of an SM busy for (k-steps x 16 DMMA x 16 cycles) / 4 sub-partitions x
     // 4 warps = k-steps x 256 cycles; co-resident CTAs start that far apart (options.stagger, default on)
     int64_t ksteps = 0;
@@ -543,8 +570,12 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t, std::vector<GatherDes
                          ? (int) std::min<int64_t>(ksteps * 256 + 8192, 50000000)
                          : 0;
     need_partial = P.box_list ? std::max<int64_t>(P.nlist, 1) : padded; // one partial per evaluated box
-    // DMMAs issued: every evaluated box runs all k-steps of all terms on its full (padded) extent
-    executed = (double) nboxes * (double) box_elems * 2.0 * 4.0 * (double) ksteps;
+    // DMMA flops issued (512 per DMMA.8x8x4): per k-step a warp with work issues 16 DMMAs, 8 in the boundary layer of an odd
+    // hole tile; warps of a ragged last tile-particle box without a valid slot issue none
+    int64_t ksteps_x = 0;
+    for(int i = 0; i < P.nterms_x; i++) ksteps_x += (int64_t) (P.term[i].kslabs - 1) * 4 + P.term[i].ksteps_last;
+    const double sub_groups = (double) (P.sub[0] * P.sub[1] * P.sub[2]);
+    executed = 512.0 * sub_groups * (units_x * (double) ksteps_x + units_y * (double) (ksteps - ksteps_x));
   }
   b.nparts = need_partial;
   if(need_partial > b.partial_cap) {

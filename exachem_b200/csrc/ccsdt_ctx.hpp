@@ -157,6 +157,7 @@ struct ccsdt_ctx {
   struct BoxList {
     int32_t* dev = nullptr;
     int32_t  n   = 0;
+    double   units_x = 0, units_y = 0; // sum over the listed boxes of (DMMAs per k-step and warp) x (warps with work), layout X / Y terms
   };
   std::map<std::array<int, 19>, BoxList> box_lists;
   // node-shared block directory (ccsdt_share.cu); NULL = private store

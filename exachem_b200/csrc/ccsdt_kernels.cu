@@ -268,12 +268,19 @@ using Int = std::integral_constant<int, N>;
 // All K slabs of one contraction for one consumer warp.
 // acc index = (((i1*2 + i2)*2 + i3)*2 + ql)*2 + r  with i* the hole offsets inside the warp group's
 // (2,2,2) sub-box, ql the warp's tile-particle slot and r the DMMA column parity.
-template<int HH, bool A_HPP>
+// SKIP: boundary boxes of an ODD hole extent hold one valid hole index where the sub-box has two slots; the second slot
+// of that hole is then left out altogether -- SKIP = 1: it is the HPP hole (hx = 1), 2 / 3: the first / second HHP hole
+// (ga = 1 / gb = 1) -- half the fragments, half the DMMAs.  These are separate, smaller instantiations of the loop (a
+// predicate per DMMA costs more than it saves: ptxas guards every predicated mma.sync with a convergence barrier); the
+// host orders the boxes by class (interior first, then the boundary layers hole by hole), so that the CTAs of an SM run
+// the same few instantiations at any time and the instruction cache is not thrashed.
+template<int HH, bool A_HPP, int SKIP>
 __device__ __forceinline__ void consume_term(double (&acc)[32], const TaskParams& p, const TermDev& td,
                                              Ring& ring, uint32_t ring_base, uint32_t full_bar,
                                              uint32_t empty_bar, const int sub_off[3], int wq, int lane) {
   constexpr int HA = (HH == 0) ? 1 : 0;        // the two other holes, ascending
   constexpr int HB = (HH == 2) ? 1 : 2;
+  constexpr int NHX = SKIP == 1 ? 1 : 2, NGA = SKIP == 2 ? 1 : 2, NGB = SKIP == 3 ? 1 : 2;
   const int     q  = frag_row(lane >> 2), l3 = lane & 3;
   // lane part of the swizzled fragment address (see DESIGN.md "shared-memory layout"): fragment row
   // lane>>2 lives in shared-memory row frag_row(lane>>2) of its 8-row group, so that the 16 lanes of
@@ -311,8 +318,8 @@ __device__ __forceinline__ void consume_term(double (&acc)[32], const TaskParams
   for(int x = 0; x < 2; x++)
 #pragma unroll
     for(int y = 0; y < 2; y++) {
-      fh[x][y] = lds_f64(base + (jx << 5) + hpp_off[x][y]);
-      fg[x][y] = lds_f64(base + (jx << 5) + hhp_off[x][y]);
+      if(x < NHX) fh[x][y] = lds_f64(base + (jx << 5) + hpp_off[x][y]);
+      if(x < NGA && y < NGB) fg[x][y] = lds_f64(base + (jx << 5) + hhp_off[x][y]);
     }
 
   for(int s = 0; s < td.kslabs; s++) {
@@ -330,19 +337,19 @@ __device__ __forceinline__ void consume_term(double (&acc)[32], const TaskParams
       }
       else jn = base + (((j + 1) ^ jx) << 5);
 #pragma unroll
-      for(int hx = 0; hx < 2; hx++)
+      for(int hx = 0; hx < NHX; hx++)
 #pragma unroll
         for(int ql = 0; ql < 2; ql++) {
 #pragma unroll
-          for(int ga = 0; ga < 2; ga++)
+          for(int ga = 0; ga < NGA; ga++)
 #pragma unroll
-            for(int gb = 0; gb < 2; gb++) {
+            for(int gb = 0; gb < NGB; gb++) {
               int hi[3];
               hi[HH] = hx, hi[HA] = ga, hi[HB] = gb;
               const int ai = ((((hi[0] * 2 + hi[1]) * 2 + hi[2]) * 2 + ql) * 2);
               if(A_HPP) dmma884(acc[ai], acc[ai + 1], fh[hx][ql], fg[ga][gb]);
               else dmma884(acc[ai], acc[ai + 1], fg[ga][gb], fh[hx][ql]);
-              if(hx == 1 && ql == 1) fg[ga][gb] = lds_f64(jn + hhp_off[ga][gb]);
+              if(hx == NHX - 1 && ql == 1) fg[ga][gb] = lds_f64(jn + hhp_off[ga][gb]);
             }
           fh[hx][ql] = lds_f64(jn + hpp_off[hx][ql]);
         }
@@ -353,16 +360,39 @@ __device__ __forceinline__ void consume_term(double (&acc)[32], const TaskParams
   }
 }
 
+// a warp none of whose tile-particle slots lies inside the tile (ragged last box of p4 / p5) has no DMMA to issue for the
+// term: it only keeps the ring protocol (wait for every slab, hand it back)
+__device__ __forceinline__ void consume_idle(const TaskParams& p, const TermDev& td, Ring& ring, uint32_t full_bar,
+                                             uint32_t empty_bar) {
+  for(int s = 0; s < td.kslabs; s++) {
+    mbar_wait(full_bar + 8 * ring.stage, ring.phase, p.error_flag, 1);
+    mbar_arrive(empty_bar + 8 * ring.stage);
+    ring.advance((uint32_t) p.stages);
+  }
+}
+
+// jb: the hole (0..2) whose second slot of this warp's sub-box lies outside the tile, -1 = none
+template<int HH, bool A_HPP>
+__device__ __forceinline__ void consume_skip(double (&acc)[32], const TaskParams& p, const TermDev& td, Ring& ring,
+                                             uint32_t ring_base, uint32_t full_bar, uint32_t empty_bar, const int sub_off[3],
+                                             int wq, int lane, int jb) {
+  constexpr int HA = (HH == 0) ? 1 : 0;
+  if(jb < 0) consume_term<HH, A_HPP, 0>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane);
+  else if(jb == HH) consume_term<HH, A_HPP, 1>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane);
+  else if(jb == HA) consume_term<HH, A_HPP, 2>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane);
+  else consume_term<HH, A_HPP, 3>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane);
+}
+
 __device__ __forceinline__ void consume_dispatch(double (&acc)[32], const TaskParams& p, const TermDev& td,
                                                  Ring& ring, uint32_t ring_base, uint32_t full_bar,
-                                                 uint32_t empty_bar, const int sub_off[3], int wq, int lane) {
+                                                 uint32_t empty_bar, const int sub_off[3], int wq, int lane, int jb) {
   switch(td.hpp_hole * 2 + td.a_is_hpp) {
-    case 0: consume_term<0, false>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane); break;
-    case 1: consume_term<0, true>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane); break;
-    case 2: consume_term<1, false>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane); break;
-    case 3: consume_term<1, true>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane); break;
-    case 4: consume_term<2, false>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane); break;
-    default: consume_term<2, true>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane); break;
+    case 0: consume_skip<0, false>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane, jb); break;
+    case 1: consume_skip<0, true>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane, jb); break;
+    case 2: consume_skip<1, false>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane, jb); break;
+    case 3: consume_skip<1, true>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane, jb); break;
+    case 4: consume_skip<2, false>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane, jb); break;
+    default: consume_skip<2, true>(acc, p, td, ring, ring_base, full_bar, empty_bar, sub_off, wq, lane, jb); break;
   }
 }
 
@@ -520,6 +550,18 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
     double         acc[32];
 #pragma unroll
     for(int i = 0; i < 32; i++) acc[i] = 0.0;
+    // boundary layers of the tile (see consume_term): the hole whose second slot is outside, and whether this warp's
+    // two tile-particle slots are both outside in layout X (p4) / Y (p5)
+    int jb = -1;
+#pragma unroll
+    for(int j = 2; j >= 0; j--)
+      if(bc.off[j] + sub_off[j] + 1 >= p.ext[j]) jb = j;
+#ifdef CCSDT_NO_BOUNDARY_VARIANTS // A/B builds (tools/ab_build.sh)
+    jb = -1;
+    const bool idle_x = false, idle_y = false;
+#else
+    const bool idle_x = bc.off[3] + 2 * wq >= p.ext[3], idle_y = bc.off[4] + 2 * wq >= p.ext[4];
+#endif
 
     for(int t = 0; t < p.nterms; t++) {
       if(relayout && t == p.nterms_x) {
@@ -560,7 +602,8 @@ __global__ void __launch_bounds__(MAXT, MINB) fused_t_dmma_kernel(const __grid_c
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
       }
-      consume_dispatch(acc, p, p.term[t], ring, ring_base, full_bar, empty_bar, sub_off, wq, lane);
+      if(t < p.nterms_x ? idle_x : idle_y) consume_idle(p, p.term[t], ring, full_bar, empty_bar);
+      else consume_dispatch(acc, p, p.term[t], ring, ring_base, full_bar, empty_bar, sub_off, wq, lane, jb);
     }
 
     // ---------------- epilogue: denominators, E[T], then the s1 part of E(T) ----------------
