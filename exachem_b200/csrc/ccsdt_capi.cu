@@ -620,7 +620,10 @@ int stage_task(ccsdt_ctx* ctx, StageBuf& b, const Task& t, std::vector<GatherDes
       }
   }
   // blocks fetched for this task (and any prefetched earlier) are still on their way: one event, no host wait
+  const bool fenced = ctx->fetch_dirty || !ctx->sym_check_pending.empty();
   if(int rc2 = fetch_fence(ctx, ctx->s_stage)) return rc2;
+  if(fenced)
+    if(int rc2 = flush_block_symmetry_checks(ctx)) return rc2; // behind the fence: the blocks have landed
   // the buffer's partials and box-scheduler words are zeroed here, on the staging stream, long before the launch
   // (ids of the padded brick grid that are not boxes are never written: their partials stay zero)
   CK(launch_zero(b.d_partial, 2 * b.nparts, b.d_counter, COUNTER_WORDS, ctx->s_stage));
@@ -945,6 +948,8 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
     if(flag) return ctx->fail("device error flag " + std::to_string(flag), 9);
     if(ctx->opt.symmetry && ctx->opt.check_symmetry >= 0) {
       CK(cudaStreamSynchronize(ctx->s_fetch));
+      if(int rc = flush_block_symmetry_checks(ctx)) return rc; // blocks prefetched for tasks this run did not reach
+      CK(cudaStreamSynchronize(ctx->s_stage));
       CK(cudaMemcpy(&flag, ctx->d_symflag, 4, cudaMemcpyDeviceToHost));
       if(flag)
         return ctx->fail("an operand is not antisymmetric (T2 in (a,b) / (i,j), v2ijab in (i,j) / (a,b), v2ijka in (i,j), v2iabc in (b,c)): "

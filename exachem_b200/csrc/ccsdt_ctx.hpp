@@ -140,6 +140,7 @@ struct ccsdt_ctx {
   uint32_t*       d_error = nullptr;   // [0] error word of the fused kernel, [1..2] watchdog limit, [3] unused
   uint32_t*       d_symflag = nullptr; // set by antisym_check_kernel: an operand is not antisymmetric (options.symmetry)
   bool            dense_check_pending[5] = {false, false, false, false, false};
+  std::vector<ccsdt::BlockKey> sym_check_pending; // fetched blocks whose antisymmetry check has not been queued yet
   cudaStream_t    s_compute = nullptr, s_compute2 = nullptr, s_stage = nullptr;
   cudaEvent_t     ev_base = nullptr;   // start of the current run: kernel intervals are placed on its time line
   double          kernel_busy_until = 0.0; // end (ms after ev_base) of the union of fused-kernel intervals so far
@@ -213,6 +214,7 @@ int  fetch_fence(ccsdt_ctx* ctx, cudaStream_t st);
 // queues the antisymmetry checks (options.symmetry / check_symmetry) of a storage block on `st`, of the dense tensors on s_stage
 int  check_block_symmetry(ccsdt_ctx* ctx, const BlockKey& key, const double* dev, cudaStream_t st);
 int  check_dense_symmetry(ccsdt_ctx* ctx);
+int  flush_block_symmetry_checks(ccsdt_ctx* ctx); // queues the checks of the blocks fetched since the last call on s_stage
 
 // ---- ccsdt_share.cu ----
 int    share_acquire(ccsdt_ctx* ctx, const BlockKey& key, size_t bytes, double** dev, int* slab, size_t* offset, void** entry);

@@ -109,6 +109,7 @@ int clear_blocks(ccsdt_ctx* ctx, bool keep_pinned) {
     it = ctx->blocks.erase(it);
   }
   ctx->fetch_dirty = false;
+  ctx->sym_check_pending.clear();
   return 0;
 }
 
@@ -293,7 +294,9 @@ int resolve_block(ccsdt_ctx* ctx, const BlockKey& key, size_t elems, int64_t for
     it = ctx->blocks.emplace(key, be).first;
     if(int rc = share_publish_after(ctx, dir_entry, ctx->s_fetch)) return rc;
     }
-    if(int rc = check_block_symmetry(ctx, key, dev, ctx->s_fetch)) return rc;
+    // (checked later, on the staging stream: a kernel on the fetch stream would have to wait for a slot among the fused
+    //  CTAs and hold every copy queued behind it back with it)
+    if(ctx->opt.symmetry && ctx->opt.check_symmetry >= 0) ctx->sym_check_pending.push_back(key);
   }
   it->second.last_use = std::max(it->second.last_use, for_clock);
   // row-major strides of the storage block
@@ -353,6 +356,16 @@ int check_block_symmetry(ccsdt_ctx* ctx, const BlockKey& key, const double* dev,
   return 0;
 }
 
+int flush_block_symmetry_checks(ccsdt_ctx* ctx) {
+  for(const BlockKey& key: ctx->sym_check_pending) {
+    auto it = ctx->blocks.find(key); // (a prefetched block may have been evicted again)
+    if(it == ctx->blocks.end()) continue;
+    if(int rc = check_block_symmetry(ctx, key, it->second.dev, ctx->s_stage)) return rc;
+  }
+  ctx->sym_check_pending.clear();
+  return 0;
+}
+
 int check_dense_symmetry(ccsdt_ctx* ctx) {
   for(int t = 1; t < 5; t++) {
     if(!ctx->dense_check_pending[t]) continue;
@@ -366,11 +379,27 @@ int check_dense_symmetry(ccsdt_ctx* ctx) {
       acc *= n[d];
     }
     if(ctx->upload_pending[t]) CK(cudaStreamWaitEvent(ctx->s_stage, ctx->ev_full[t], 0));
-    for(int q = 0; q < 2; q++)
-      if(kAntiPairs[t][q] >= 0) {
-        CK(launch_antisym_check(ctx->dense[t], n, stv, kAntiPairs[t][q], ctx->d_symflag, ctx->s_stage));
-        ctx->stats.kernel_launches++;
+    // Same-spin index pairs only: that is what the box skipping relies on (it applies to coinciding TILES, hence equal
+    // spins), and what the per-block check of the block store sees.  Mixed-spin blocks of a closed-shell tensor set are
+    // related by the spin flip of the solver and agree to its convergence only -- and half of them are never read.
+    for(int q = 0; q < 2; q++) {
+      const int pair = kAntiPairs[t][q];
+      if(pair < 0) continue;
+      const bool virt = kinds[pair] == 'v';
+      int64_t    lo   = 0;
+      for(int spin = 1; spin <= 2; spin++) {
+        int     tb, te;
+        int64_t cnt = 0;
+        ctx->sp.spin_range(virt, spin, tb, te, cnt);
+        if(cnt > 0) {
+          int64_t m[4] = {n[0], n[1], n[2], n[3]};
+          m[pair] = m[pair + 1] = cnt;
+          CK(launch_antisym_check(ctx->dense[t] + lo * stv[pair] + lo * stv[pair + 1], m, stv, pair, ctx->d_symflag, ctx->s_stage));
+          ctx->stats.kernel_launches++;
+        }
+        lo += cnt;
       }
+    }
   }
   return 0;
 }
