@@ -456,3 +456,29 @@ def test_asynchronous_dense_upload_gives_identical_energies(cfg):
             assert 0 < st["h2d_bytes"] < sum(T[k].nbytes for k in ("t1", "t2", "v2ijab", "v2ijka", "v2iabc"))
     finally:
         ctx.close()
+
+
+def test_n60v500_full_tile_task_matches_the_reference_cpu_golden():
+    """Kernel task 0 of the north_star problem -- (nocc, nvir) = (60, 500), ccsdt_tilesize 32, all six tiles full: the 32^6 task,
+    the largest tile the reference CPU kernel can index -- against the energy the REFERENCE's own CPU path gave on the same
+    procedural tensors (tests/golden/n60v500_ts32_task0.json, made by tests/golden/make_n60v500_task0_golden.py in two hours
+    of CPU).  The synthetic energies are of order 4e5, so the 1e-9 Eh bar of real molecules (|E(T)| ~ 1e-2 Eh, i.e. 1e-7
+    relative) is applied as a relative bound, tightened to 1e-11; with the symmetry reduction (36-fold here) and without."""
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "n60v500_ts32_task0.json")))
+    sp = drv.setup_mo_space(60, 60, 500, 500, 32)
+    evl = syn.Orbitals(60, 60, 500, 500).orbital_energies()
+    for symmetry in (1, 0):
+        ctx = drv.Context(0)
+        try:
+            ctx.set_options(symmetry=symmetry)
+            ctx.set_space(sp, evl, True)
+            ctx.set_synthetic(1234)
+            tasks, _, _ = drv.enumerate_tasks(sp, True)
+            assert list(tasks[0][:6]) == g["task"]
+            e1, e2, st, _ = ctx.run_tasks([0])
+        finally:
+            ctx.close()
+        r1, r2 = abs(e1 - g["E[T]"]) / abs(g["E[T]"]), abs(e2 - g["E(T)"]) / abs(g["E(T)"])
+        print(f"(60,500) task 0, symmetry {symmetry}: relative deviation from the reference CPU kernel {r1:.2e} / {r2:.2e}")
+        assert r1 < 1e-11 and r2 < 1e-11, (e1, e2, g)
+
