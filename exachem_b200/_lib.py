@@ -32,6 +32,12 @@ class Stats(C.Structure):
                 ("blocks_from_peers", C.c_int64), ("peer_bytes", C.c_int64)]
 
 
+class MemoryEstimate(C.Structure):
+    _fields_ = [("exec_max_hole_tile", C.c_int64), ("exec_max_particle_tile", C.c_int64), ("panel_bytes", C.c_int64),
+                ("s1_bytes", C.c_int64), ("task_block_bytes", C.c_int64), ("tensor_bytes", C.c_int64 * 5),
+                ("minimum_bytes", C.c_int64)]
+
+
 FETCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, _u32p, _dp, C.c_size_t)
 
 SIGNATURES = {
@@ -46,6 +52,7 @@ SIGNATURES = {
     "ccsdt_count_ops": (C.c_int, [C.c_int, C.c_int, _i32p, _i64p, C.c_int, C.POINTER(C.c_longdouble)]),
     "ccsdt_partition": (C.c_int, [C.c_int, C.c_int, _i32p, _i64p, C.c_int, C.c_int, _i32p, C.c_int64]),
     "ccsdt_check_memory": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "ccsdt_estimate_memory": (C.c_int, [C.c_int] * 4 + [_i64p, _i32p, C.c_int, C.POINTER(MemoryEstimate)]),
     "ccsdt_box_weight": (C.c_int, [C.c_int, _i32p]),
     "ccsdt_set_space": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [_i64p, _i32p, _dp, C.c_int]),
     "ccsdt_put_dense": (C.c_int, [C.c_void_p, C.c_int, _dp]),

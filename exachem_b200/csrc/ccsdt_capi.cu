@@ -1290,6 +1290,24 @@ int ccsdt_check_memory(int tilesize, int nbf, size_t gpu_bytes, size_t* required
   return need < (double) gpu_bytes ? 0 : 1;
 }
 
+int ccsdt_estimate_memory(int noa, int nob, int nva, int nvb, const int64_t* k_range, const int32_t* k_spin, int target,
+                          ccsdt_memory_estimate* out) {
+  if(!k_range || !k_spin || !out) return 1;
+  const Space store = make_space(noa, nob, nva, nvb, k_range, k_spin, nullptr, true);
+  if(!store.validate().empty()) return 1;
+  const Space          ex     = target ? make_exec_space(store, target) : store;
+  const int            sub[3] = {1, 1, 1};
+  const MemoryEstimate e      = estimate_memory(ex, sub, 2);
+  out->exec_max_hole_tile     = ex.max_hole_tile();
+  out->exec_max_particle_tile = ex.max_particle_tile();
+  out->panel_bytes            = e.panel_bytes;
+  out->s1_bytes               = e.s1_bytes;
+  out->task_block_bytes       = e.task_block_bytes;
+  for(int t = 0; t < 5; t++) out->tensor_bytes[t] = e.tensor_bytes[t];
+  out->minimum_bytes = e.minimum_bytes;
+  return 0;
+}
+
 int ccsdt_set_space(ccsdt_ctx* ctx, int noa, int nob, int nva, int nvb, const int64_t* k_range, const int32_t* k_spin,
                     const double* evl, int is_restricted) {
   if(!ctx || !k_range || !k_spin || !evl) return 1;

@@ -364,4 +364,57 @@ int canonical_block(int tensor, uint32_t bid[4], int perm[4]) {
   return sign;
 }
 
+// ------------------------------------------------------------------------------------------------
+MemoryEstimate estimate_memory(const Space& sp, const int sub[3], int staging_buffers) {
+  auto up = [](int64_t x, int64_t m) { return (x + m - 1) / m * m; };
+  MemoryEstimate e{};
+  int64_t        thp = 0;
+  for(int i = 0; i < 3; i++) thp = std::max(thp, up(sp.max_hole_tile(), 2 * std::max(sub[i], 1)));
+  e.thp = up(thp, 2);
+  e.tpp = up(sp.max_particle_tile(), 8);
+  int     tb, te;
+  int64_t na, nb;
+  sp.spin_range(false, 1, tb, te, na);
+  sp.spin_range(false, 2, tb, te, nb);
+  e.kp_occ = up(std::max<int64_t>(std::max(na, nb), 1), 16);
+  const int64_t occ_spin = std::max(na, nb);
+  sp.spin_range(true, 1, tb, te, na);
+  sp.spin_range(true, 2, tb, te, nb);
+  e.kp_virt = up(std::max<int64_t>(std::max(na, nb), 1), 16);
+  const int64_t virt_spin = std::max(na, nb);
+  // per staging buffer: 9 slots x (HPP [THp][TPp][TPp][Kp] + HHP [THp][THp][TPp][Kp]) for the d1 (Kp_occ) and d2 (Kp_virt) pools
+  const int64_t hpp = 9 * e.thp * e.tpp * e.tpp, hhp = 9 * e.thp * e.thp * e.tpp;
+  e.panel_bytes     = (int64_t) staging_buffers * 8 * (hpp + hhp) * (e.kp_occ + e.kp_virt);
+  e.s1_bytes        = (int64_t) staging_buffers * 8 * (9 * e.thp * e.tpp + 9 * e.tpp * e.tpp * e.thp * e.thp);
+  // one task reads at most 9 (T2 + V) block pairs per contracted tile; summed over the contracted tiles of one spin that
+  // is 9 x 2 x T^3 x (orbitals of the spin) elements for d1 and for d2, plus the 9 s1 pairs
+  const int64_t th = sp.max_hole_tile(), tp = sp.max_particle_tile();
+  e.task_block_bytes = 8 * (9 * (th * tp * tp + th * th * tp) * occ_spin + 9 * (th * th * tp + th * tp * tp) * virt_spin +
+                            9 * (th * tp + th * th * tp * tp));
+  // spin-conserving blocks: T1 s_a = s_i; four-index tensors s0 + s1 = s2 + s3 (6 of the 16 spin patterns)
+  int64_t n[2][2]; // [occ, virt][alpha, beta]
+  for(int part = 0; part < 2; part++)
+    for(int spin = 1; spin <= 2; spin++) {
+      int64_t c = 0;
+      sp.spin_range(part == 1, spin, tb, te, c);
+      n[part][spin - 1] = c;
+    }
+  auto four = [&](int k0, int k1, int k2, int k3) { // kinds: 0 = occupied, 1 = virtual
+    int64_t tot = 0;
+    for(int pat = 0; pat < 16; pat++) {
+      const int s0 = (pat >> 3) & 1, s1 = (pat >> 2) & 1, s2 = (pat >> 1) & 1, s3 = pat & 1;
+      if(s0 + s1 != s2 + s3) continue;
+      tot += n[k0][s0] * n[k1][s1] * n[k2][s2] * n[k3][s3];
+    }
+    return 8 * tot;
+  };
+  e.tensor_bytes[0] = 8 * (n[1][0] * n[0][0] + n[1][1] * n[0][1]);
+  e.tensor_bytes[1] = four(1, 1, 0, 0);
+  e.tensor_bytes[2] = four(0, 0, 1, 1);
+  e.tensor_bytes[3] = four(0, 0, 0, 1);
+  e.tensor_bytes[4] = four(0, 1, 1, 1);
+  e.minimum_bytes   = e.panel_bytes + e.s1_bytes + 2 * e.task_block_bytes;
+  return e;
+}
+
 } // namespace ccsdt

@@ -108,6 +108,19 @@ struct TilePiece {
 // particle = the dimension is virtual; exec_tile / store_tile are global tile ids of their spaces
 std::vector<TilePiece> split_tile(const Space& exec, const Space& store, int exec_tile);
 
+// ---- device memory the path needs (host-only arithmetic; mirrors ensure_pools of ccsdt_capi.cu) -----------------
+// What the reference prints before the (T) loop is the HOST memory of its staging buffers and block caches
+// (exachem/cc/ccsd_t/ccsd_t.cpp:95-152); here the staging lives in HBM.
+struct MemoryEstimate {
+  int64_t thp, tpp, kp_occ, kp_virt; // padded panel extents: hole / particle tile, contraction lengths (d1 / d2)
+  int64_t panel_bytes;               // K-major operand panels (d1 + d2, HPP + HHP, 9 slots each), all staging buffers
+  int64_t s1_bytes;                  // staged s1 operands, all staging buffers
+  int64_t task_block_bytes;          // upper bound of the tensor blocks ONE task reads (what must be resident to stage it)
+  int64_t tensor_bytes[5];           // spin-conserving blocks of T1, T2, v2ijab, v2ijka, v2iabc: a fully resident block store
+  int64_t minimum_bytes;             // panels + s1 + blocks of the task in flight and of the task being staged
+};
+MemoryEstimate estimate_memory(const Space& exec, const int sub[3], int staging_buffers);
+
 // The blocks the reference requests are canonically ordered: T2{p_lo,p_hi,h_lo,h_hi},
 // v2ijka{h_lo,h_hi,h7,p}, v2iabc{h,p7,p_lo,p_hi}, v2ijab{h_hi,h_lo,p_hi,p_lo}.  A storage sub-block of a diagonal
 // execution block may come out in the other order; canonical_block swaps the offending pair(s) of `bid`, records the

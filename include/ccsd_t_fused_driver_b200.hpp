@@ -186,6 +186,19 @@ std::tuple<T, T, double, double> CCSD_T_Fused_Driver<T>::execute(
   check(ccsdt_set_space(ctx, s.noa, s.nob, s.nva, s.nvb, s.k_range.data(), s.k_spin.data(), evl.data(),
                         is_restricted ? 1 : 0));
 
+  if(opt.verbose >= 1 && rank == 0) {
+    // the counterpart of the reference's memory summary (ccsd_t.cpp:95-152): what the path takes of this GPU's HBM
+    ccsdt_memory_estimate m;
+    if(ccsdt_estimate_memory(s.noa, s.nob, s.nva, s.nvb, s.k_range.data(), s.k_spin.data(), opt.exec_tilesize, &m) == 0)
+      std::fprintf(stderr,
+                   "[CCSD(T) B200] execution tiles up to %lld (occ) / %lld (virt); HBM per GPU: operand panels %.2f GiB, s1 %.2f GiB, "
+                   "blocks of one task <= %.2f GiB (minimum %.2f GiB); T2 %.1f, v2ijab %.1f, v2ijka %.1f, v2iabc %.1f GiB if fully resident\n",
+                   (long long) m.exec_max_hole_tile, (long long) m.exec_max_particle_tile, m.panel_bytes / 1073741824.0,
+                   m.s1_bytes / 1073741824.0, m.task_block_bytes / 1073741824.0, m.minimum_bytes / 1073741824.0,
+                   m.tensor_bytes[1] / 1073741824.0, m.tensor_bytes[2] / 1073741824.0, m.tensor_bytes[3] / 1073741824.0,
+                   m.tensor_bytes[4] / 1073741824.0);
+  }
+
   FetchUser<T> user;
   user.tensor[CCSDT_T1]     = &d_t1;
   user.tensor[CCSDT_T2]     = &d_t2;

@@ -153,6 +153,19 @@ CCSDT_API int     ccsdt_partition(int noab, int nvab, const int32_t* k_spin, con
                         int is_restricted, int nranks, int32_t* owner /* one per kernel task */,
                         int64_t cap);
 CCSDT_API int     ccsdt_check_memory(int tilesize, int nbf, size_t gpu_bytes, size_t* required);
+/* host-only: the HBM the path will use for a tile space -- the counterpart of the memory summary the reference prints before
+ * the (T) loop for its host-side staging buffers and block caches (exachem/cc/ccsd_t/ccsd_t.cpp:95-152).  `target` is
+ * options.exec_tilesize (0: the caller's tiles).  All sizes in bytes. */
+typedef struct ccsdt_memory_estimate {
+  int64_t exec_max_hole_tile, exec_max_particle_tile; /* largest execution tiles */
+  int64_t panel_bytes;      /* K-major operand panels of the two staging buffers */
+  int64_t s1_bytes;         /* staged s1 operands of the two staging buffers */
+  int64_t task_block_bytes; /* upper bound of the tensor blocks one task reads */
+  int64_t tensor_bytes[5];  /* spin-conserving blocks of T1, T2, v2ijab, v2ijka, v2iabc (a fully resident block store) */
+  int64_t minimum_bytes;    /* panels + s1 + the blocks of two tasks: below this the LRU thrashes */
+} ccsdt_memory_estimate;
+CCSDT_API int     ccsdt_estimate_memory(int noa, int nob, int nva, int nvb, const int64_t* k_range, const int32_t* k_spin,
+                                        int target, ccsdt_memory_estimate* out);
 /* permutation weight the fused kernel gives CTA box `box` (box coordinates along h1,h2,h3,p4,p5,p6) under
  * symmetry bits `sym` (bit 0: tiles h1b==h2b, 1: h2b==h3b, 2: p4b==p5b, 3: p5b==p6b); 0 = the box is the
  * mirror image of an evaluated one and is skipped.  Summed over a tile's boxes the weights count every box once.

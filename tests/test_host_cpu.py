@@ -124,3 +124,30 @@ def test_box_weight_skips_the_triple_hole_diagonal():
     n = [5, 5, 5, 2, 3, 2]
     total = sum(L.ccsdt_box_weight(3 | 16, (C.c_int32 * 6)(*b)) for b in itertools.product(*[range(k) for k in n]))
     assert total == int(np.prod(n)) - 5 * 2 * 3 * 2       # the 5 diagonal hole boxes of every particle box are dropped
+
+
+def test_memory_estimate_matches_the_survey_sizes():
+    """ccsdt_estimate_memory (the counterpart of the memory summary of ccsd_t.cpp:95-152): tensor sizes of SURVEY.md 8d at
+    (60,500) -- T2 and v2ijab 43 GB, v2ijka 5.2 GB, v2iabc 360 GB, 2.7 GB of blocks per task -- and the panel pools"""
+    import ctypes as C
+    L = _lib.load()
+
+    def est(o, v, ts, target):
+        sp = drv.setup_mo_space(o, o, v, v, ts)
+        m = _lib.MemoryEstimate()
+        kr, ks = np.ascontiguousarray(sp.k_range, np.int64), np.ascontiguousarray(sp.k_spin, np.int32)
+        assert L.ccsdt_estimate_memory(sp.noa, sp.nob, sp.nva, sp.nvb, kr.ctypes.data_as(_lib._i64p),
+                                       ks.ctypes.data_as(_lib._i32p), target, C.byref(m)) == 0
+        return m
+
+    m = est(60, 500, 32, 0)
+    assert [round(x / 1e9, 1) for x in m.tensor_bytes] == [0.0, 43.2, 43.2, 5.2, 360.0]
+    assert m.tensor_bytes[4] == 6 * 60 * 500 ** 3 * 8
+    assert abs(m.task_block_bytes / 1e9 - 2.7) < 0.1
+    # two staging buffers x 9 slots x (HPP 32*32*32 + HHP 32*32*32) x (Kp 64 + 512) doubles
+    assert m.panel_bytes == 2 * 8 * 9 * (32 ** 3 + 32 ** 3) * (64 + 512)
+    assert m.minimum_bytes == m.panel_bytes + m.s1_bytes + 2 * m.task_block_bytes
+    caf_own, caf_exec = est(51, 195, 28, 0), est(51, 195, 28, -1)
+    assert (caf_own.exec_max_particle_tile, caf_exec.exec_max_particle_tile) == (28, 40)
+    assert caf_own.tensor_bytes[:] == caf_exec.tensor_bytes[:]           # the tensors do not depend on the execution tiling
+
