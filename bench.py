@@ -541,6 +541,13 @@ def main():
             dt2, agg2, e_e2e = timed(step_e2e, n2, 1)
             for k in shim_env:
                 os.environ.pop(k, None)
+            if world > 1:
+                dist.barrier()
+                if rank == 0:
+                    try:
+                        os.unlink(f"/dev/shm/tamm_shim_{key}")
+                    except OSError:
+                        pass
             if not dense_host:
                 info = np.zeros(3, np.int64)
                 H.L.adapter_table_info(table, info.ctypes.data_as(_lib._i64p))
