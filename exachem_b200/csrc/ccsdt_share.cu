@@ -13,7 +13,8 @@
 //     copy has completed (a host function queued behind the copy on the fetch stream).  FETCHING elsewhere: it waits a
 //     few milliseconds for the owner's upload, then copies from it; past 50 ms it fetches a private copy instead.
 //   * The owner never evicts a block with readers; a reader drops its count when its copy has completed.
-//   * Detach: a barrier among the attached ranks (nobody is still reading), then mappings are closed and slabs freed.
+//   * Detach is collective: barrier (nobody is still reading), every rank closes its mappings, barrier, only then the
+//     owners free their slabs (freeing exported memory that an importer still has open is undefined), barrier, unmap.
 #include "ccsdt_ctx.hpp"
 
 #include <fcntl.h>
@@ -69,6 +70,7 @@ struct ShareState {
   std::vector<Slab> slabs;
   std::map<size_t, std::vector<std::pair<int, size_t>>> free_list; // exact-size reuse: block sizes repeat heavily
   std::map<std::pair<int, int>, void*>                  peer_base; // (rank, slab) -> mapped base
+  std::vector<ShareEntry*>                              mine;      // directory entries this rank has claimed
 };
 
 // runs on a CUDA callback thread when the copy queued before it on the fetch stream has completed: an upload publishes
@@ -253,6 +255,7 @@ int share_acquire(ccsdt_ctx* ctx, const BlockKey& key, size_t bytes, double** de
       e->offset = *offset;
       e->bytes  = bytes;
       *entry    = e;
+      s->mine.push_back(e);
     }
     share_unlock(s);
     return 0;
@@ -293,6 +296,7 @@ void share_detach(ccsdt_ctx* ctx) {
   share_poll(ctx, true);
   share_barrier(s); // nobody reads anybody's slabs any more
   for(auto& kv: s->peer_base) cudaIpcCloseMemHandle(kv.second);
+  share_barrier(s); // every importer has closed its mappings: only now may the exporters free (CUDA IPC rule)
   // every block of the shared store goes with its slab
   for(auto it = ctx->blocks.begin(); it != ctx->blocks.end();) {
     if(it->second.slab >= 0) {
@@ -302,8 +306,8 @@ void share_detach(ccsdt_ctx* ctx) {
     else ++it;
   }
   share_lock(s);
-  for(uint32_t i = 0; i < s->hdr->capacity; i++)
-    if(s->table[i].key && s->table[i].owner == s->rank) s->table[i].state = kTomb;
+  for(ShareEntry* e: s->mine)
+    if(e->owner == s->rank && e->state != kTomb) e->state = kTomb; // (an entry another rank has taken over since is not ours)
   s->hdr->ranks[s->rank].nslabs = 0;
   share_unlock(s);
   if(ctx->s_stage) cudaStreamSynchronize(ctx->s_stage);

@@ -182,6 +182,7 @@ std::tuple<T, T, double, double> CCSD_T_Fused_Driver<T>::execute(
   if(const char* e = std::getenv("CCSDT_B200_SYMMETRY")) opt.symmetry = std::atoi(e) != 0;
   if(const char* e = std::getenv("CCSDT_B200_EXEC_TILESIZE")) opt.exec_tilesize = std::atoi(e);
   if(const char* e = std::getenv("CCSDT_B200_VERBOSE")) opt.verbose = std::atoi(e); // 2: per-task trace on stderr
+  if(const char* e = std::getenv("CCSDT_B200_BLOCK_BUDGET_MB")) opt.block_budget_bytes = (int64_t) (std::atof(e) * 1048576.0);
   check(ccsdt_set_options(ctx, &opt));
   check(ccsdt_set_space(ctx, s.noa, s.nob, s.nva, s.nvb, s.k_range.data(), s.k_spin.data(), evl.data(),
                         is_restricted ? 1 : 0));

@@ -45,4 +45,4 @@ rc = L.adapter_ccsdt_execute(sp.noa, sp.nob, sp.nva, sp.nvb, kr.ctypes.data_as(_
                              int(g["restricted"]), g["tilesize"], out.ctypes.data_as(_lib._dp), gets.ctypes.data_as(_lib._i64p), None,
                              C.byref(st))
 json.dump({"rc": rc, "err": L.adapter_last_error().decode(), "e1": out[0], "e2": out[1], "tasks_run": st.tasks_run,
-           "blocks_fetched": st.blocks_fetched, "blocks_from_peers": st.blocks_from_peers, "gets": int(gets.sum()), "rank": rank}, open(out_path, "w"))
+           "blocks_fetched": st.blocks_fetched, "blocks_from_peers": st.blocks_from_peers, "blocks_evicted": st.blocks_evicted, "gets": int(gets.sum()), "rank": rank}, open(out_path, "w"))

@@ -103,3 +103,18 @@ def test_internal_nccl_allreduce_through_the_cpp_header(tmp_path):
     assert all(r["rc"] == 0 for r in res), res
     for r in res:
         assert abs(r["e1"] - float(g["energy1"])) <= 1e-9 and abs(r["e2"] - float(g["energy2"])) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_node_shared_block_store_evicts_under_a_small_budget(tmp_path):
+    """the shared store with 64 KB of HBM per rank (the working set is larger): blocks are evicted -- never while a peer is
+    copying them --, their directory entries are tombstoned and reused, evicted blocks come back from the host or from the
+    other rank, and the energies stay within the bar"""
+    name = "h2o_shape_ts7"
+    g = GOLD[name]
+    res = launch(2, "execute", name, tmp_path, env_extra={"CCSDT_B200_DYNAMIC": "0", "CCSDT_B200_BLOCK_BUDGET_MB": "0.0625"})
+    for r in res:
+        assert r["rc"] == 0, r
+        assert abs(r["e1"] - float(g["energy1"])) <= 1e-9 and abs(r["e2"] - float(g["energy2"])) <= 1e-9
+    assert sum(r["blocks_evicted"] for r in res) > 0
+
