@@ -27,6 +27,18 @@
  *                           (energy1 = E[T], energy2 = E(T)) the caller reduces at ccsd_t.cpp:262-263
  *   ccsdt_set_task_counter <- AtomicCounterGA (allocate / fetch_add / deallocate) ccsd_t_fused_driver.hpp:169-172,456,541
  *   ccsdt_check_memory   <- check_memory_req                 exachem/cc/ccsd_t/hybrid.cpp:19-41
+ *   ccsdt_estimate_memory <- the memory summary printed before the (T) loop   exachem/cc/ccsd_t/ccsd_t.cpp:95-152
+ *   options.exec_tilesize, ccsdt_exec_tiles, ccsdt_make_exec_tiles
+ *                        <- the caller's re-tiling of T1/T2/V2 for ccsdt_tilesize   exachem/cc/ccsd_t/ccsd_t.cpp:168-193
+ *                           (execution tiles are cut inside the library; blocks are still requested in the caller's tiling)
+ *   ccsdt_task_counter_open / _close <- AtomicCounterGA allocate / deallocate among the ranks of a node
+ *                           ccsd_t_fused_driver.hpp:169-172,541
+ *   ccsdt_share_attach / _detach <- every rank's own Tensor<T>::get of the same block and its per-rank host caches
+ *                           exachem/cc/ccsd_t/ccsd_t.cpp:236-241 (one fetch per node, GPU-to-GPU copies for the other ranks)
+ *   ccsdt_comm_unique_id / _init / _allreduce / _destroy <- ec.pg().reduce(&energy1 / &energy2, ReduceOp::sum, 0)
+ *                           exachem/cc/ccsd_t/ccsd_t.cpp:262-263 (ncclAllReduce of the two energies)
+ *   ccsdt_clear_blocks, ccsdt_release_cached <- the per-call allocation and release of all staging memory in execute
+ *                           ccsd_t_fused_driver.hpp:197-250,495-530
  *
  * Conventions: plain pointers and sizes, no C++ or torch types.  Every function returns 0 on success
  * and a non-zero code on failure; ccsdt_last_error() gives the message.  (The reference's convention
