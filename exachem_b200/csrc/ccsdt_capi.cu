@@ -842,9 +842,9 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
     // Prefetch (static hand-out, blocks through the callback): while the host would only wait for the GPU to
     // release a staging buffer, it pulls the blocks of the tasks to come into HBM -- the callback (the caller's
     // Tensor::get) runs on this thread, its copies travel on s_fetch.  It runs as far ahead as the block budget
-    // allows (options.prefetch_tasks bounds it in tasks): the order of order_for_fetch puts the fetch-heavy tasks
-    // last, and their blocks arrive under the long kernels before them.  Blocks of future tasks carry their future
-    // clock, so the LRU does not take them back before they are used.
+    // allows (options.prefetch_tasks bounds it in tasks): order_for_fetch starts with the units that need the fewest
+    // bytes, and the blocks of the bigger ones arrive under the kernels before them.  Blocks of future tasks carry
+    // their future clock, so the LRU does not take them back before they are used.
     const int64_t lookahead = (!ctx->task_counter && fetching && ctx->opt.prefetch_tasks >= 0)
                                 ? (ctx->opt.prefetch_tasks > 0 ? ctx->opt.prefetch_tasks : ((int64_t) 1 << 40)) : 0;
     // Dynamic hand-out: the next task is not known before it is claimed, so a rank claims ONE task ahead and fetches
@@ -951,6 +951,7 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
       if(int rc = flush_block_symmetry_checks(ctx)) return rc; // blocks prefetched for tasks this run did not reach
       CK(cudaStreamSynchronize(ctx->s_stage));
       CK(cudaMemcpy(&flag, ctx->d_symflag, 4, cudaMemcpyDeviceToHost));
+      if(flag) CK(cudaMemset(ctx->d_symflag, 0, 4)); // reported once: the caller may replace the operands and run again
       if(flag)
         return ctx->fail("an operand is not antisymmetric (T2 in (a,b) / (i,j), v2ijab in (i,j) / (a,b), v2ijka in (i,j), v2iabc in (b,c)): "
                          "options.symmetry = 1 relies on it -- set symmetry = 0 to evaluate every element as the reference does", 12);
