@@ -951,7 +951,7 @@ static int run_task_list(ccsdt_ctx* ctx, const std::vector<int64_t>& ids, bool u
       if(int rc = flush_block_symmetry_checks(ctx)) return rc; // blocks prefetched for tasks this run did not reach
       CK(cudaStreamSynchronize(ctx->s_stage));
       CK(cudaMemcpy(&flag, ctx->d_symflag, 4, cudaMemcpyDeviceToHost));
-      if(flag) CK(cudaMemset(ctx->d_symflag, 0, 4)); // reported once: the caller may replace the operands and run again
+      // (the verdict stays until ccsdt_set_space drops the operands: a block that failed is not looked at again)
       if(flag)
         return ctx->fail("an operand is not antisymmetric (T2 in (a,b) / (i,j), v2ijab in (i,j) / (a,b), v2ijka in (i,j), v2iabc in (b,c)): "
                          "options.symmetry = 1 relies on it -- set symmetry = 0 to evaluate every element as the reference does", 12);

@@ -114,7 +114,8 @@ typedef struct ccsdt_options {
   int32_t check_symmetry; /* with symmetry = 1: 0 (default) = verify on the device, once per block / dense tensor as it arrives,
                             that T2, v2ijab (both index pairs), v2ijka (i,j) and v2iabc (b,c) are antisymmetric where that can be
                             seen inside one block (blocks whose two tiles coincide; whole tensors for ccsdt_put_dense) -- the run
-                            fails with a message instead of returning an energy built on a wrong assumption; -1 = skip the check */
+                            fails with a message instead of returning an energy built on a wrong assumption, and keeps failing
+                            until ccsdt_set_space replaces the operands; -1 = skip the check */
 } ccsdt_options;
 
 typedef struct ccsdt_stats {
